@@ -1,0 +1,166 @@
+/*
+ * liftreg_b200.h -- C-ABI of the B200-native LiftReg resampling library
+ * (libliftreg_b200.so, built from liftreg_b200/csrc/ for sm_100a).
+ *
+ * The reference (uncbiag/LiftReg) is pure Python: its "operator API" for this
+ * path is the Python surface of
+ *     src/liftreg/utils/sdct_projection_utils.py   ("sdct" below)
+ *     src/liftreg/utils/net_utils.py               (Bilinear, identity_map)
+ *     src/liftreg/layers/layers.py                 (proj_layer)
+ *     src/liftreg/models/LiftRegDeformSubspaceBackproj.py:85-93,68-69
+ * and every one of those bottoms out in torch.nn.functional.grid_sample.
+ * Each entry point below replaces the cited reference lines; the Python mirror
+ * in liftreg_b200/ binds them with ctypes (INTEGRATION.md shows the stub a
+ * reference maintainer would add).
+ *
+ * Conventions
+ *   - plain C types only; no torch / C++ types cross this boundary.
+ *   - every buffer is owned by the caller; the library never allocates or frees
+ *     device memory and keeps no state (geometry is passed by value per call).
+ *   - all tensors are dense, C-contiguous fp32 unless a stride is given.
+ *   - functions without the _host suffix take DEVICE pointers, are asynchronous
+ *     on `stream` (a cudaStream_t) and never synchronise.
+ *   - _host functions take HOST pointers (pinned for full speed) plus a device
+ *     workspace of lr_*_workspace_bytes(); they enqueue H2D, kernels and D2H on
+ *     `stream` and synchronise it before returning, like the reference calls
+ *     they replace (which end in .cpu().numpy()).
+ *   - return 0 on success, a negative lr_status on failure; never throws or
+ *     exits.  lr_last_error() returns a thread-local message.
+ *   - volume axes (d,w,h) = (axial, coronal, sagittal); detector (rd,rh);
+ *     emitter poses in voxel units, detector plane y = 0 (sdct:59-68).
+ */
+#ifndef LIFTREG_B200_H
+#define LIFTREG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define LR_API __attribute__((visibility("default")))
+#else
+#define LR_API
+#endif
+
+typedef void *lr_stream_t; /* cudaStream_t */
+
+typedef enum {
+    LR_OK = 0,
+    LR_ERR_BAD_ARGUMENT = -1,
+    LR_ERR_CUDA = -2,
+    LR_ERR_WORKSPACE = -3,
+    LR_ERR_NO_DEVICE = -4
+} lr_status;
+
+enum { LR_PAD_ZEROS = 0, LR_PAD_BORDER = 1 };     /* net_utils.py:21  zero_boundary ? zeros : border */
+enum { LR_MODE_LINEAR = 0, LR_MODE_NEAREST = 1 }; /* net_utils.py:23  mode = "bilinear" | "nearest"  */
+enum { LR_YNORM_WM1 = 0, LR_YNORM_W = 1 };        /* sdct:55 (/(w-1))  vs  layers.py:234 (/w)        */
+
+/* ---- library ---------------------------------------------------------- */
+LR_API int lr_abi_version(void);
+LR_API const char *lr_last_error(void);
+/* number of CUDA devices visible, or a negative lr_status */
+LR_API int lr_device_count(void);
+/* kernels launched by this library (all threads) since the last reset (bench.py's gpu_launches) */
+LR_API long long lr_launch_count(void);
+LR_API void lr_launch_count_reset(void);
+
+/* ---- cone-beam DRR ---------------------------------------------------- */
+/* replaces sdct:59-86 calculate_projection (grid build sdct:15-57, flip :76, grid_sample+sum+*dx :81, *0.1 :85)
+ * and layers.py:182-187 proj_layer.forward (y_norm_mode = LR_YNORM_W, out_scale = 1).
+ *   vol   (B,d,w,h)       attenuation volume(s)
+ *   poses (n_pose_sets,P,3) HOST pointer, float64, voxel units; n_pose_sets is 1 (shared by all B, as in
+ *         proj_layer) or B (per item, models/previous/RegNet2D3D.py:161-171)
+ *   proj  (B,P,rd,rh) = out_scale * dx[p,u,v] * sum_j trilinear_zeros(vol[b], ray point j)   */
+LR_API int lr_drr_forward(const float *vol, int B, int d, int w, int h,
+                          const double *poses, int n_pose_sets, int P, int rd, int rh,
+                          const float spacing[3], int y_norm_mode, float out_scale,
+                          float *proj, lr_stream_t stream);
+
+/* adjoint of lr_drr_forward wrt vol (autograd of sdct:81 / layers.py:187; RegNet2D3D.py:161-185 needs it).
+ * grad_vol (B,d,w,h) is ACCUMULATED into (caller zero-initialises). */
+LR_API int lr_drr_backward(const float *grad_proj, int B, int d, int w, int h,
+                           const double *poses, int n_pose_sets, int P, int rd, int rh,
+                           const float spacing[3], int y_norm_mode, float out_scale,
+                           float *grad_vol, lr_stream_t stream);
+
+/* replaces sdct:15-57 project_grid_multi / layers.py:194-236 (API parity and bit-exactness checks; the DRR
+ * kernels never materialise this).  grid (P,rd,rh,w,3) nullable, dx (P,rd,rh) nullable.
+ * flip != 0 writes the last axis reversed, as sdct:76 / forward_grids (sdct:223,263) return it. */
+LR_API int lr_project_grid(const double *poses, int P, int rd, int rh, int d, int w, int h,
+                           const float spacing[3], int y_norm_mode, int flip,
+                           float *grid, float *dx, lr_stream_t stream);
+
+/* host-buffer form of lr_drr_forward == calculate_projection's numpy-in / numpy-out contract (sdct:59-100). */
+LR_API size_t lr_drr_forward_host_workspace_bytes(int B, int d, int w, int h, int P, int rd, int rh);
+LR_API int lr_drr_forward_host(const float *vol_host, int B, int d, int w, int h,
+                               const double *poses, int n_pose_sets, int P, int rd, int rh,
+                               const float spacing[3], int y_norm_mode, float out_scale,
+                               float *proj_host, void *workspace, size_t workspace_bytes, lr_stream_t stream);
+
+/* ---- backprojection ---------------------------------------------------- */
+/* replaces sdct:227-250 backproj_grids_with_poses + the grid_sample block at
+ * models/LiftRegDeformSubspaceBackproj.py:85-93 (same block: models/previous/RegNet2D3D.py:105-112).
+ *   proj  (B,P,pw,ph)
+ *   poses (P,3) HOST pointer, float32 (Registration2D3DDataset.py:121 casts to fp32; geometry frozen from
+ *         batch item 0, model :85-87)
+ *   out[b*out_batch_stride + p*out_chan_stride + (i*w+j)*h+k] = bilinear_zeros(proj[b,p], u(p,i,j), v(p,j,k))
+ *   strides are in elements; a dense (B,P,d,w,h) output uses P*d*w*h and d*w*h.  They let the caller aim at
+ *   channels 1..P of the (B,1+P,d,w,h) encoder input and skip torch.cat (model :95-98). */
+LR_API int lr_backproject_forward(const float *proj, const float *poses, int B, int P, int pw, int ph,
+                                  int d, int w, int h, float *out,
+                                  int64_t out_batch_stride, int64_t out_chan_stride, lr_stream_t stream);
+
+/* adjoint wrt proj; grad_proj (B,P,pw,ph) is ACCUMULATED into (caller zero-initialises). */
+LR_API int lr_backproject_backward(const float *grad_out, int64_t go_batch_stride, int64_t go_chan_stride,
+                                   const float *poses, int B, int P, int pw, int ph, int d, int w, int h,
+                                   float *grad_proj, lr_stream_t stream);
+
+/* replaces sdct:227-250 itself: grid (P,2,d,w,h), channel 0 = detector axis 1 (ph), channel 1 = axis 0 (pw). */
+LR_API int lr_backproj_grid(const float *poses, int P, int d, int w, int h, int pw, int ph,
+                            float *grid, lr_stream_t stream);
+
+LR_API size_t lr_backproject_forward_host_workspace_bytes(int B, int P, int pw, int ph, int d, int w, int h);
+LR_API int lr_backproject_forward_host(const float *proj_host, const float *poses, int B, int P, int pw, int ph,
+                                       int d, int w, int h, float *out_host,
+                                       void *workspace, size_t workspace_bytes, lr_stream_t stream);
+
+/* ---- displacement-field warp ------------------------------------------- */
+/* replaces net_utils.py:26-56 Bilinear.forward / forward_stn.
+ *   img (B,C,D,H,W); phi (B,3,D,H,W), channel c addresses volume axis c in [-1,1] (the channel reversal of
+ *   :27-30 is folded into the addressing); out (B,C,D,H,W).
+ *   using_scale: sample (img+1)/2 and return 2*out-1 (:48-52), fused.
+ *   disp_plus_identity != 0: phi holds the DISPLACEMENT and the normalised identity map
+ *   (net_utils.py:59-87) is added in-kernel, i.e. the `disp_field + self.id_transform` of model :68 is fused;
+ *   the sum is rounded to fp32 exactly as the torch add would. */
+LR_API int lr_warp_forward(const float *img, const float *phi, int B, int C, int D, int H, int W,
+                           int padding, int mode, int using_scale, int disp_plus_identity,
+                           float *out, lr_stream_t stream);
+
+/* adjoint (autograd of grid_sample at net_utils.py:32-35 plus the (x+1)/2 and *2-1 factors).
+ * grad_img (B,C,D,H,W) nullable, ACCUMULATED into (caller zero-initialises);
+ * grad_phi (B,3,D,H,W) nullable, overwritten (zero for LR_MODE_NEAREST). */
+LR_API int lr_warp_backward(const float *grad_out, const float *img, const float *phi,
+                            int B, int C, int D, int H, int W,
+                            int padding, int mode, int using_scale, int disp_plus_identity,
+                            float *grad_img, float *grad_phi, lr_stream_t stream);
+
+/* replaces net_utils.py:59-87 identity_map: out (3,D,H,W) */
+LR_API int lr_identity_map(int D, int H, int W, float *out, lr_stream_t stream);
+
+LR_API size_t lr_warp_forward_host_workspace_bytes(int B, int C, int D, int H, int W);
+LR_API int lr_warp_forward_host(const float *img_host, const float *phi_host, int B, int C, int D, int H, int W,
+                                int padding, int mode, int using_scale, int disp_plus_identity, float *out_host,
+                                void *workspace, size_t workspace_bytes, lr_stream_t stream);
+
+/* ---- HU -> attenuation -------------------------------------------------- */
+/* replaces sdct:6-13 calc_relative_atten_coef(_cuda): mu = (max(HU,-1000)+1000)/1000*0.2; in place allowed */
+LR_API int lr_atten_coef(const float *hu, int64_t n, float *mu, lr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIFTREG_B200_H */

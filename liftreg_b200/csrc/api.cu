@@ -1,0 +1,137 @@
+// Library plumbing of libliftreg_b200.so: error reporting, launch accounting and the host-buffer entry
+// points (the numpy-in / numpy-out contract of the reference calls, e.g. sdct:59-100 calculate_projection).
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace lr {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};   // process-wide: autograd runs backward on its own thread
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_launch(const char *what) {
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+        return LR_ERR_CUDA;
+    }
+    return LR_OK;
+}
+
+static size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
+
+static int cuda_ok(cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return LR_OK;
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return LR_ERR_CUDA;
+}
+
+}  // namespace lr
+
+using namespace lr;
+
+extern "C" int lr_abi_version(void) { return 1; }
+extern "C" const char *lr_last_error(void) { return g_err; }
+extern "C" long long lr_launch_count(void) { return g_launches.load(); }
+extern "C" void lr_launch_count_reset(void) { g_launches.store(0); }
+
+extern "C" int lr_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        set_error("cudaGetDeviceCount: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        return LR_ERR_NO_DEVICE;
+    }
+    return n;
+}
+
+// ---- DRR, host buffers ----------------------------------------------------------------------------
+extern "C" size_t lr_drr_forward_host_workspace_bytes(int B, int d, int w, int h, int P, int rd, int rh) {
+    if (B <= 0 || d <= 0 || w <= 0 || h <= 0 || P <= 0 || rd <= 0 || rh <= 0) return 0;
+    return align256(sizeof(float) * (size_t)B * d * w * h) + align256(sizeof(float) * (size_t)B * P * rd * rh);
+}
+
+extern "C" int lr_drr_forward_host(const float *vol_host, int B, int d, int w, int h, const double *poses,
+                                   int n_pose_sets, int P, int rd, int rh, const float spacing[3], int y_norm_mode,
+                                   float out_scale, float *proj_host, void *workspace, size_t workspace_bytes,
+                                   lr_stream_t stream) {
+    LR_REQUIRE(vol_host && proj_host && workspace, "drr_forward_host: null pointer");
+    const size_t need = lr_drr_forward_host_workspace_bytes(B, d, w, h, P, rd, rh);
+    if (need == 0 || workspace_bytes < need) {
+        set_error("drr_forward_host: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
+        return LR_ERR_WORKSPACE;
+    }
+    cudaStream_t st = as_stream(stream);
+    const size_t vol_bytes = sizeof(float) * (size_t)B * d * w * h, proj_bytes = sizeof(float) * (size_t)B * P * rd * rh;
+    float *d_vol = (float *)workspace;
+    float *d_proj = (float *)((char *)workspace + align256(vol_bytes));
+    if (int e = cuda_ok(cudaMemcpyAsync(d_vol, vol_host, vol_bytes, cudaMemcpyHostToDevice, st), "drr_forward_host: H2D")) return e;
+    if (int e = lr_drr_forward(d_vol, B, d, w, h, poses, n_pose_sets, P, rd, rh, spacing, y_norm_mode, out_scale, d_proj, stream)) return e;
+    if (int e = cuda_ok(cudaMemcpyAsync(proj_host, d_proj, proj_bytes, cudaMemcpyDeviceToHost, st), "drr_forward_host: D2H")) return e;
+    return cuda_ok(cudaStreamSynchronize(st), "drr_forward_host: sync");   // sdct:97 .cpu() is synchronous
+}
+
+// ---- backprojection, host buffers -------------------------------------------------------------------
+extern "C" size_t lr_backproject_forward_host_workspace_bytes(int B, int P, int pw, int ph, int d, int w, int h) {
+    if (B <= 0 || P <= 0 || pw <= 0 || ph <= 0 || d <= 0 || w <= 0 || h <= 0) return 0;
+    return align256(sizeof(float) * (size_t)B * P * pw * ph) + align256(sizeof(float) * (size_t)B * P * d * w * h);
+}
+
+extern "C" int lr_backproject_forward_host(const float *proj_host, const float *poses, int B, int P, int pw, int ph,
+                                           int d, int w, int h, float *out_host, void *workspace,
+                                           size_t workspace_bytes, lr_stream_t stream) {
+    LR_REQUIRE(proj_host && out_host && workspace, "backproject_forward_host: null pointer");
+    const size_t need = lr_backproject_forward_host_workspace_bytes(B, P, pw, ph, d, w, h);
+    if (need == 0 || workspace_bytes < need) {
+        set_error("backproject_forward_host: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
+        return LR_ERR_WORKSPACE;
+    }
+    cudaStream_t st = as_stream(stream);
+    const size_t in_bytes = sizeof(float) * (size_t)B * P * pw * ph, out_bytes = sizeof(float) * (size_t)B * P * d * w * h;
+    float *d_in = (float *)workspace;
+    float *d_out = (float *)((char *)workspace + align256(in_bytes));
+    if (int e = cuda_ok(cudaMemcpyAsync(d_in, proj_host, in_bytes, cudaMemcpyHostToDevice, st), "backproject_forward_host: H2D")) return e;
+    if (int e = lr_backproject_forward(d_in, poses, B, P, pw, ph, d, w, h, d_out, (int64_t)P * d * w * h, (int64_t)d * w * h, stream)) return e;
+    if (int e = cuda_ok(cudaMemcpyAsync(out_host, d_out, out_bytes, cudaMemcpyDeviceToHost, st), "backproject_forward_host: D2H")) return e;
+    return cuda_ok(cudaStreamSynchronize(st), "backproject_forward_host: sync");
+}
+
+// ---- warp, host buffers -----------------------------------------------------------------------------
+extern "C" size_t lr_warp_forward_host_workspace_bytes(int B, int C, int D, int H, int W) {
+    if (B <= 0 || C <= 0 || D <= 0 || H <= 0 || W <= 0) return 0;
+    const size_t nv = (size_t)D * H * W;
+    return 2 * align256(sizeof(float) * B * C * nv) + align256(sizeof(float) * B * 3 * nv);
+}
+
+extern "C" int lr_warp_forward_host(const float *img_host, const float *phi_host, int B, int C, int D, int H, int W,
+                                    int padding, int mode, int using_scale, int disp_plus_identity, float *out_host,
+                                    void *workspace, size_t workspace_bytes, lr_stream_t stream) {
+    LR_REQUIRE(img_host && phi_host && out_host && workspace, "warp_forward_host: null pointer");
+    const size_t need = lr_warp_forward_host_workspace_bytes(B, C, D, H, W);
+    if (need == 0 || workspace_bytes < need) {
+        set_error("warp_forward_host: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
+        return LR_ERR_WORKSPACE;
+    }
+    cudaStream_t st = as_stream(stream);
+    const size_t nv = (size_t)D * H * W;
+    const size_t img_bytes = sizeof(float) * B * C * nv, phi_bytes = sizeof(float) * B * 3 * nv;
+    float *d_img = (float *)workspace;
+    float *d_phi = (float *)((char *)workspace + align256(img_bytes));
+    float *d_out = (float *)((char *)d_phi + align256(phi_bytes));
+    if (int e = cuda_ok(cudaMemcpyAsync(d_img, img_host, img_bytes, cudaMemcpyHostToDevice, st), "warp_forward_host: H2D img")) return e;
+    if (int e = cuda_ok(cudaMemcpyAsync(d_phi, phi_host, phi_bytes, cudaMemcpyHostToDevice, st), "warp_forward_host: H2D phi")) return e;
+    if (int e = lr_warp_forward(d_img, d_phi, B, C, D, H, W, padding, mode, using_scale, disp_plus_identity, d_out, stream)) return e;
+    if (int e = cuda_ok(cudaMemcpyAsync(out_host, d_out, img_bytes, cudaMemcpyDeviceToHost, st), "warp_forward_host: D2H")) return e;
+    return cuda_ok(cudaStreamSynchronize(st), "warp_forward_host: sync");
+}

@@ -1,0 +1,249 @@
+// Backprojection: lift P detector images into a P-channel volume (per-voxel gather over views), sm_100a.
+//
+// Replaces reference src/liftreg/utils/sdct_projection_utils.py:227-250 (backproj_grids_with_poses, a
+// 131 MB (1,P,2,d,w,h) grid) and the grid_sample block of
+// src/liftreg/models/LiftRegDeformSubspaceBackproj.py:85-93.  The voxel->detector map is evaluated in
+// registers with the reference's fp32 op order:
+//     x_i = i - d/2,  y_j = w-1-j (reversed, sdct:232),  z_k = k - h/2
+//     scale = sy / (sy - y_j)                                   (sdct:239)
+//     gu = ((x_i - sx)*scale + sx) / pw * 2                     (sdct:241-242,247)   -> detector axis 0
+//     gv = ((z_k - sz)*scale + sz) / ph * 2                     (sdct:248)           -> detector axis 1
+// and sampled like ATen's vectorised CPU grid_sampler_2d (align_corners, zeros):
+//     ix = (g+1)*((S-1)/2); w = ix-floor(ix); e = 1-w; ... out = fma(se_v,n*w, fma(sw_v,n*e, fma(ne_v,s*w, nw_v*(s*e))))
+//
+// Work decomposition: the v-part of the map depends on (p,j,k), the u-part on (p,i,j).  A thread owns one k
+// (lanes along h: coalesced 128 B stores, near-contiguous gathers), keeps its v-part in registers and walks a
+// chunk of i; the per-i u-part comes from a small shared-memory table built once per block.  The batch loop is
+// innermost, so geometry and weights are shared by all B items.
+#include "common.cuh"
+
+namespace lr {
+
+constexpr int BP_MAX_VIEWS = 64;   // views per launch (poses travel as kernel parameters)
+constexpr int BP_ICHUNK = 32;      // i-planes per block
+
+struct BpPoses {
+    float s[BP_MAX_VIEWS][3];
+};
+
+struct BpDims {
+    int B, P, pw, ph, d, w, h;
+    int p0;                        // first view of this launch
+    float half_d, half_h;          // d/2, h/2 (exact)
+    float pwf, phf;                // (float)pw, (float)ph
+    float hpw, hph;                // (pw-1)/2, (ph-1)/2
+    int64_t proj_view_stride;      // pw*ph
+    int64_t out_batch_stride, out_chan_stride;
+};
+
+struct AxisTap {      // one axis of the bilinear footprint
+    int i0;           // floor index (may be out of range)
+    float w1;         // ix - floor(ix)
+};
+
+// normalised coordinate -> (floor index, upper weight), ATen vector-kernel order
+__device__ __forceinline__ AxisTap axis_tap(float centred, float s_c, float scale, float sizef, float half_sm1) {
+    float a = add_rn(mul_rn(sub_rn(centred, s_c), scale), s_c);   // (x - s)*scale + s
+    float g = mul_rn(div_rn(a, sizef), 2.0f);                     // / size * 2
+    float ix = mul_rn(add_rn(g, 1.0f), half_sm1);                 // (g+1)*((S-1)/2)
+    float fl = floorf(ix);
+    AxisTap t;
+    t.i0 = __float2int_rd(ix);
+    t.w1 = sub_rn(ix, fl);
+    return t;
+}
+
+__device__ __forceinline__ float view_scale(float sy, int w, int j) {
+    float y = (float)(w - 1 - j);
+    return div_rn(sy, sub_rn(sy, y));
+}
+
+__global__ void __launch_bounds__(256)
+    backproject_forward_kernel(const float *__restrict__ proj, float *__restrict__ out, BpDims g, BpPoses poses) {
+    __shared__ int s_row[BP_ICHUNK];     // row index iu0 of the detector for plane i
+    __shared__ float s_wn[BP_ICHUNK];    // n = iy - floor(iy)
+
+    const int j = blockIdx.x;
+    const int i_begin = blockIdx.y * BP_ICHUNK;
+    const int pl = blockIdx.z;           // view inside this launch
+    const int p = g.p0 + pl;
+    const float sx = poses.s[pl][0], sy = poses.s[pl][1], sz = poses.s[pl][2];
+    const float scale = view_scale(sy, g.w, j);
+    const int i_count = min(BP_ICHUNK, g.d - i_begin);
+
+    if (threadIdx.x < i_count) {
+        AxisTap t = axis_tap((float)(i_begin + (int)threadIdx.x) - g.half_d, sx, scale, g.pwf, g.hpw);
+        s_row[threadIdx.x] = t.i0;
+        s_wn[threadIdx.x] = t.w1;
+    }
+    __syncthreads();
+
+    const float *pv = proj + (int64_t)p * g.proj_view_stride;
+    const int64_t proj_batch = (int64_t)g.P * g.proj_view_stride;
+    for (int k = threadIdx.x; k < g.h; k += blockDim.x) {
+        AxisTap tv = axis_tap((float)k - g.half_h, sz, scale, g.phf, g.hph);
+        const float wq = tv.w1, e = sub_rn(1.0f, wq);
+        const bool c0 = (unsigned)tv.i0 < (unsigned)g.ph, c1 = (unsigned)(tv.i0 + 1) < (unsigned)g.ph;
+        float *o = out + (int64_t)p * g.out_chan_stride + ((int64_t)i_begin * g.w + j) * g.h + k;
+        for (int ii = 0; ii < i_count; ++ii) {
+            const int r0 = s_row[ii];
+            const float n = s_wn[ii], s = sub_rn(1.0f, n);
+            const bool rv0 = (unsigned)r0 < (unsigned)g.pw, rv1 = (unsigned)(r0 + 1) < (unsigned)g.pw;
+            const float nw = mul_rn(s, e), ne = mul_rn(s, wq), sw = mul_rn(n, e), se = mul_rn(n, wq);
+            const float *row0 = pv + (int64_t)r0 * g.ph + tv.i0;
+            const float *row1 = row0 + g.ph;
+            for (int b = 0; b < g.B; ++b) {
+                const float *q0 = row0 + b * proj_batch, *q1 = row1 + b * proj_batch;
+                const float va = (rv0 && c0) ? __ldg(q0) : 0.0f;
+                const float vb = (rv0 && c1) ? __ldg(q0 + 1) : 0.0f;
+                const float vc = (rv1 && c0) ? __ldg(q1) : 0.0f;
+                const float vd = (rv1 && c1) ? __ldg(q1 + 1) : 0.0f;
+                const float r = fma_rn(vd, se, fma_rn(vc, sw, fma_rn(vb, ne, mul_rn(va, nw))));
+                st_stream(o + b * g.out_batch_stride, r);
+            }
+            o += (int64_t)g.w * g.h;
+        }
+    }
+}
+
+// Adjoint wrt the projections: scatter grad_out * weight into the 4 detector taps (RED.ADD.F32).
+__global__ void __launch_bounds__(256)
+    backproject_backward_kernel(const float *__restrict__ gout, float *__restrict__ gproj, BpDims g, BpPoses poses) {
+    __shared__ int s_row[BP_ICHUNK];
+    __shared__ float s_wn[BP_ICHUNK];
+    const int j = blockIdx.x;
+    const int i_begin = blockIdx.y * BP_ICHUNK;
+    const int pl = blockIdx.z;
+    const int p = g.p0 + pl;
+    const float sx = poses.s[pl][0], sy = poses.s[pl][1], sz = poses.s[pl][2];
+    const float scale = view_scale(sy, g.w, j);
+    const int i_count = min(BP_ICHUNK, g.d - i_begin);
+    if (threadIdx.x < i_count) {
+        AxisTap t = axis_tap((float)(i_begin + (int)threadIdx.x) - g.half_d, sx, scale, g.pwf, g.hpw);
+        s_row[threadIdx.x] = t.i0;
+        s_wn[threadIdx.x] = t.w1;
+    }
+    __syncthreads();
+    float *pv = gproj + (int64_t)p * g.proj_view_stride;
+    const int64_t proj_batch = (int64_t)g.P * g.proj_view_stride;
+    for (int k = threadIdx.x; k < g.h; k += blockDim.x) {
+        AxisTap tv = axis_tap((float)k - g.half_h, sz, scale, g.phf, g.hph);
+        const float wq = tv.w1, e = sub_rn(1.0f, wq);
+        const bool c0 = (unsigned)tv.i0 < (unsigned)g.ph, c1 = (unsigned)(tv.i0 + 1) < (unsigned)g.ph;
+        const float *o = gout + (int64_t)p * g.out_chan_stride + ((int64_t)i_begin * g.w + j) * g.h + k;
+        for (int ii = 0; ii < i_count; ++ii) {
+            const int r0 = s_row[ii];
+            const float n = s_wn[ii], s = sub_rn(1.0f, n);
+            const bool rv0 = (unsigned)r0 < (unsigned)g.pw, rv1 = (unsigned)(r0 + 1) < (unsigned)g.pw;
+            const float nw = mul_rn(s, e), ne = mul_rn(s, wq), sw = mul_rn(n, e), se = mul_rn(n, wq);
+            float *row0 = pv + (int64_t)r0 * g.ph + tv.i0;
+            float *row1 = row0 + g.ph;
+            for (int b = 0; b < g.B; ++b) {
+                const float go = ld_stream(o + b * g.out_batch_stride);
+                float *q0 = row0 + b * proj_batch, *q1 = row1 + b * proj_batch;
+                if (rv0 && c0) red_add(q0, mul_rn(nw, go));
+                if (rv0 && c1) red_add(q0 + 1, mul_rn(ne, go));
+                if (rv1 && c0) red_add(q1, mul_rn(sw, go));
+                if (rv1 && c1) red_add(q1 + 1, mul_rn(se, go));
+            }
+            o += (int64_t)g.w * g.h;
+        }
+    }
+}
+
+// sdct:227-250 itself, for API parity: grid (P,2,d,w,h); channel 0 = gv (detector axis 1), channel 1 = gu.
+__global__ void __launch_bounds__(256) backproj_grid_kernel(float *__restrict__ grid, BpDims g, BpPoses poses) {
+    const int j = blockIdx.x, i = blockIdx.y, pl = blockIdx.z, p = g.p0 + pl;
+    const float sx = poses.s[pl][0], sy = poses.s[pl][1], sz = poses.s[pl][2];
+    const float scale = view_scale(sy, g.w, j);
+    const int64_t nv = (int64_t)g.d * g.w * g.h;
+    const float xi = (float)i - g.half_d;
+    const float gu = mul_rn(div_rn(add_rn(mul_rn(sub_rn(xi, sx), scale), sx), g.pwf), 2.0f);
+    for (int k = threadIdx.x; k < g.h; k += blockDim.x) {
+        const float zk = (float)k - g.half_h;
+        const float gv = mul_rn(div_rn(add_rn(mul_rn(sub_rn(zk, sz), scale), sz), g.phf), 2.0f);
+        const int64_t vox = ((int64_t)i * g.w + j) * g.h + k;
+        grid[((int64_t)p * 2 + 0) * nv + vox] = gv;
+        grid[((int64_t)p * 2 + 1) * nv + vox] = gu;
+    }
+}
+
+static int fill_dims(BpDims &g, int B, int P, int pw, int ph, int d, int w, int h, int64_t obs, int64_t ocs) {
+    LR_REQUIRE(B > 0 && P > 0 && pw > 0 && ph > 0 && d > 0 && w > 0 && h > 0,
+               "backproject: non-positive dimension (B=%d P=%d pw=%d ph=%d d=%d w=%d h=%d)", B, P, pw, ph, d, w, h);
+    LR_REQUIRE(d <= 65535 * BP_ICHUNK && w < (1 << 30), "backproject: volume too large for the launch grid");
+    g.B = B; g.P = P; g.pw = pw; g.ph = ph; g.d = d; g.w = w; g.h = h; g.p0 = 0;
+    g.half_d = (float)((double)d / 2.0); g.half_h = (float)((double)h / 2.0);
+    g.pwf = (float)pw; g.phf = (float)ph;
+    g.hpw = (float)(pw - 1) / 2.0f; g.hph = (float)(ph - 1) / 2.0f;
+    g.proj_view_stride = (int64_t)pw * ph;
+    g.out_batch_stride = obs; g.out_chan_stride = ocs;
+    return LR_OK;
+}
+
+static int block_threads(int h) {
+    int t = ((h + 31) / 32) * 32;
+    return t < 32 ? 32 : (t > 256 ? 256 : t);
+}
+
+}  // namespace lr
+
+using namespace lr;
+
+extern "C" int lr_backproject_forward(const float *proj, const float *poses, int B, int P, int pw, int ph, int d, int w,
+                                      int h, float *out, int64_t out_batch_stride, int64_t out_chan_stride,
+                                      lr_stream_t stream) {
+    LR_REQUIRE(proj && poses && out, "backproject_forward: null pointer");
+    BpDims g;
+    if (int e = fill_dims(g, B, P, pw, ph, d, w, h, out_batch_stride, out_chan_stride)) return e;
+    LR_REQUIRE(out_chan_stride >= (int64_t)d * w * h, "backproject_forward: out_chan_stride smaller than a volume");
+    for (int p0 = 0; p0 < P; p0 += BP_MAX_VIEWS) {
+        const int np = P - p0 < BP_MAX_VIEWS ? P - p0 : BP_MAX_VIEWS;
+        BpPoses ps;
+        for (int q = 0; q < np; ++q)
+            for (int c = 0; c < 3; ++c) ps.s[q][c] = poses[(p0 + q) * 3 + c];
+        g.p0 = p0;
+        dim3 grid((unsigned)w, (unsigned)((d + BP_ICHUNK - 1) / BP_ICHUNK), (unsigned)np);
+        backproject_forward_kernel<<<grid, block_threads(h), 0, as_stream(stream)>>>(proj, out, g, ps);
+        if (int e = check_launch("backproject_forward_kernel")) return e;
+    }
+    return LR_OK;
+}
+
+extern "C" int lr_backproject_backward(const float *grad_out, int64_t go_batch_stride, int64_t go_chan_stride,
+                                       const float *poses, int B, int P, int pw, int ph, int d, int w, int h,
+                                       float *grad_proj, lr_stream_t stream) {
+    LR_REQUIRE(grad_out && poses && grad_proj, "backproject_backward: null pointer");
+    BpDims g;
+    if (int e = fill_dims(g, B, P, pw, ph, d, w, h, go_batch_stride, go_chan_stride)) return e;
+    for (int p0 = 0; p0 < P; p0 += BP_MAX_VIEWS) {
+        const int np = P - p0 < BP_MAX_VIEWS ? P - p0 : BP_MAX_VIEWS;
+        BpPoses ps;
+        for (int q = 0; q < np; ++q)
+            for (int c = 0; c < 3; ++c) ps.s[q][c] = poses[(p0 + q) * 3 + c];
+        g.p0 = p0;
+        dim3 grid((unsigned)w, (unsigned)((d + BP_ICHUNK - 1) / BP_ICHUNK), (unsigned)np);
+        backproject_backward_kernel<<<grid, block_threads(h), 0, as_stream(stream)>>>(grad_out, grad_proj, g, ps);
+        if (int e = check_launch("backproject_backward_kernel")) return e;
+    }
+    return LR_OK;
+}
+
+extern "C" int lr_backproj_grid(const float *poses, int P, int d, int w, int h, int pw, int ph, float *grid,
+                                lr_stream_t stream) {
+    LR_REQUIRE(poses && grid, "backproj_grid: null pointer");
+    BpDims g;
+    if (int e = fill_dims(g, 1, P, pw, ph, d, w, h, 0, 0)) return e;
+    LR_REQUIRE(d <= 65535, "backproj_grid: d must be <= 65535");
+    for (int p0 = 0; p0 < P; p0 += BP_MAX_VIEWS) {
+        const int np = P - p0 < BP_MAX_VIEWS ? P - p0 : BP_MAX_VIEWS;
+        BpPoses ps;
+        for (int q = 0; q < np; ++q)
+            for (int c = 0; c < 3; ++c) ps.s[q][c] = poses[(p0 + q) * 3 + c];
+        g.p0 = p0;
+        dim3 grid_dim((unsigned)w, (unsigned)d, (unsigned)np);
+        backproj_grid_kernel<<<grid_dim, block_threads(h), 0, as_stream(stream)>>>(grid, g, ps);
+        if (int e = check_launch("backproj_grid_kernel")) return e;
+    }
+    return LR_OK;
+}

@@ -1,0 +1,286 @@
+// Cone-beam DRR forward projection and its adjoint (ray-marched trilinear gather), sm_100a.
+//
+// Replaces reference src/liftreg/utils/sdct_projection_utils.py:15-57 (project_grid_multi: a materialised
+// (P,rd,rh,w,3) sample grid, 442 MB at 160^3 / 4 views / 240^2) and :59-86 (calculate_projection: flip,
+// grid_sample_3d, sum over the ray, *dx, *0.1); also src/liftreg/layers/layers.py:182-236 (proj_layer,
+// y normalised by w instead of w-1, no 0.1 factor).  Nothing is materialised: each thread owns one ray,
+// rebuilds the sample position of every coronal plane j in registers with the reference's fp32 op order
+// (so floor() indices and weights are bit-identical), gathers 8 taps through L1/L2 and accumulates in fp32
+// in ray order (j ascending).  Lanes run along the detector's second axis, which maps to the volume's
+// contiguous axis, so each warp-wide tap load touches one or two 128 B lines.
+//
+// Rays are clipped to the j-range in which they can touch the volume (a conservative superset computed from
+// the closed form X(j) = lx + j*(sx-lx)/sy); samples outside contribute exactly +0 in the reference.
+#include "common.cuh"
+
+namespace lr {
+
+constexpr int DRR_MAX_VIEWS = 128;  // (volume, pose) pairs per launch; poses travel as kernel parameters
+constexpr int DRR_ROWS = 4;         // detector rows (u) per block: 4 warps
+
+struct DrrView {
+    float sx, sy, sz;
+    int vol;  // which volume of the batch this view projects
+};
+struct DrrViews {
+    DrrView v[DRR_MAX_VIEWS];
+};
+
+struct DrrDims {
+    int d, w, h, rd, rh;
+    int view0;                 // first (b,p) pair of this launch, for output addressing
+    float half_rd, half_rh;    // rd/2, rh/2 (exact)
+    float sp0, sp1, sp2;       // voxel spacing (mm)
+    ConstDiv div_x, div_y, div_z;  // d/2, (w-1)/2 or w/2, h/2 :  X/d*2 == X/(d/2) exactly
+    float hd, hw, hh;          // (d-1)/2, (w-1)/2, (h-1)/2 : ((g+1)/2)*(S-1) == (g+1)*((S-1)/2) exactly
+    float lim_x, lim_z;        // clip half-widths d/2+2, h/2+2
+    float out_scale;
+    int64_t nvox;
+};
+
+struct Ray {
+    float sx, sy, sz, Dx, Dy, Dz, r2, dx;
+    int j0, j1;  // inclusive range of coronal planes that may touch the volume
+};
+
+__device__ __forceinline__ Ray ray_setup(const DrrView &vw, const DrrDims &g, int u, int v) {
+    Ray r;
+    r.sx = vw.sx; r.sy = vw.sy; r.sz = vw.sz;
+    const float lx = (float)u - g.half_rd, lz = (float)v - g.half_rh;   // sdct:32-33 (unit-step linspace)
+    const float Ix = add_rn(lx, -r.sx), Iy = add_rn(0.0f, -r.sy), Iz = add_rn(lz, -r.sz);  // sdct:35-38
+    const float rc = div_rn(1.0f, Iy);                                   // sdct:39
+    const float ax = mul_rn(mul_rn(Ix, rc), g.sp0), ay = mul_rn(mul_rn(Iy, rc), g.sp1), az = mul_rn(mul_rn(Iz, rc), g.sp2);
+    r.dx = __fsqrt_rn(fma_rn(az, az, fma_rn(ay, ay, mul_rn(ax, ax))));   // sdct:41 (torch CPU norm order)
+    const float n = __fsqrt_rn(fma_rn(Iz, Iz, fma_rn(Iy, Iy, mul_rn(Ix, Ix))));  // sdct:40
+    r.Dx = div_rn(Ix, n); r.Dy = div_rn(Iy, n); r.Dz = div_rn(Iz, n);
+    r.r2 = div_rn(1.0f, r.Dy);                                           // sdct:50
+
+    // conservative clip: X(j) = lx + j*(sx-lx)/sy must lie in [-lim_x, lim_x], same for Z
+    float t0 = 0.0f, t1 = (float)(g.w - 1);
+    const float inv_sy = 1.0f / r.sy;
+    const float bx = (r.sx - lx) * inv_sy, bz = (r.sz - lz) * inv_sy;
+    if (fabsf(bx) > 1e-12f) {
+        float a = (-g.lim_x - lx) / bx, b = (g.lim_x - lx) / bx;
+        t0 = fmaxf(t0, fminf(a, b)); t1 = fminf(t1, fmaxf(a, b));
+    } else if (fabsf(lx) > g.lim_x) t1 = -1.0f;
+    if (fabsf(bz) > 1e-12f) {
+        float a = (-g.lim_z - lz) / bz, b = (g.lim_z - lz) / bz;
+        t0 = fmaxf(t0, fminf(a, b)); t1 = fminf(t1, fmaxf(a, b));
+    } else if (fabsf(lz) > g.lim_z) t1 = -1.0f;
+    r.j0 = max(0, (int)floorf(t0) - 1);
+    r.j1 = min(g.w - 1, (int)ceilf(t1) + 1);
+    if (!(t1 >= t0)) { r.j0 = 0; r.j1 = -1; }
+    if (!(r.sy > (float)(g.w - 1))) { r.j0 = 0; r.j1 = g.w - 1; }  // emitter inside the slab: no clipping
+    return r;
+}
+
+struct Sample {
+    float iz, iy, ix;  // source indices along volume axes 0 (d), 1 (w), 2 (h)
+};
+
+// sdct:50-56 + flip (:76) + ATen unnormalise
+__device__ __forceinline__ Sample ray_point(const Ray &r, const DrrDims &g, int j) {
+    const float T = mul_rn(r.r2, sub_rn((float)j, r.sy));
+    const float X = add_rn(mul_rn(r.Dx, T), r.sx), Y = add_rn(mul_rn(r.Dy, T), r.sy), Z = add_rn(mul_rn(r.Dz, T), r.sz);
+    const float g0 = div_const(X, g.div_x);                  // X/d*2
+    const float g1 = add_rn(div_const(Y, g.div_y), -1.0f);   // Y/(w-1)*2 + -1
+    const float g2 = div_const(Z, g.div_z);                  // Z/h*2
+    Sample s;
+    s.iz = mul_rn(add_rn(g0, 1.0f), g.hd);
+    s.iy = mul_rn(add_rn(g1, 1.0f), g.hw);
+    s.ix = mul_rn(add_rn(g2, 1.0f), g.hh);
+    return s;
+}
+
+struct Taps {
+    float wt[8];
+    int64_t base;
+    unsigned okmask;
+};
+
+__device__ __forceinline__ Taps make_taps(const Sample &s, const DrrDims &g) {
+    const float fx = floorf(s.ix), fy = floorf(s.iy), fz = floorf(s.iz);
+    const int x0 = __float2int_rd(s.ix), y0 = __float2int_rd(s.iy), z0 = __float2int_rd(s.iz);
+    const float wx1 = sub_rn(s.ix, fx), wx0 = sub_rn(add_rn(fx, 1.0f), s.ix);
+    const float wy1 = sub_rn(s.iy, fy), wy0 = sub_rn(add_rn(fy, 1.0f), s.iy);
+    const float wz1 = sub_rn(s.iz, fz), wz0 = sub_rn(add_rn(fz, 1.0f), s.iz);
+    const float a00 = mul_rn(wx0, wy0), a10 = mul_rn(wx1, wy0), a01 = mul_rn(wx0, wy1), a11 = mul_rn(wx1, wy1);
+    Taps t;
+    t.wt[0] = mul_rn(a00, wz0); t.wt[1] = mul_rn(a10, wz0); t.wt[2] = mul_rn(a01, wz0); t.wt[3] = mul_rn(a11, wz0);
+    t.wt[4] = mul_rn(a00, wz1); t.wt[5] = mul_rn(a10, wz1); t.wt[6] = mul_rn(a01, wz1); t.wt[7] = mul_rn(a11, wz1);
+    const unsigned vx0 = (unsigned)x0 < (unsigned)g.h, vx1 = (unsigned)(x0 + 1) < (unsigned)g.h;
+    const unsigned vy0 = (unsigned)y0 < (unsigned)g.w, vy1 = (unsigned)(y0 + 1) < (unsigned)g.w;
+    const unsigned vz0 = (unsigned)z0 < (unsigned)g.d, vz1 = (unsigned)(z0 + 1) < (unsigned)g.d;
+    const unsigned mx = vx0 | (vx1 << 1);                 // bits for tx = 0,1
+    const unsigned mxy = (vy0 ? mx : 0u) | ((vy1 ? mx : 0u) << 2);
+    t.okmask = (vz0 ? mxy : 0u) | ((vz1 ? mxy : 0u) << 4);
+    t.base = ((int64_t)z0 * g.w + y0) * g.h + x0;
+    return t;
+}
+
+__global__ void __launch_bounds__(32 * DRR_ROWS)
+    drr_forward_kernel(const float *__restrict__ vol, float *__restrict__ proj, DrrDims g, DrrViews views) {
+    const int v = blockIdx.x * 32 + threadIdx.x;
+    const int u = blockIdx.y * DRR_ROWS + threadIdx.y;
+    if (v >= g.rh || u >= g.rd) return;
+    const DrrView vw = views.v[blockIdx.z];
+    const Ray r = ray_setup(vw, g, u, v);
+    const float *V = vol + (int64_t)vw.vol * g.nvox;
+    const int64_t sy = g.h, sz = (int64_t)g.w * g.h;
+
+    float acc = 0.0f;
+    for (int j = r.j0; j <= r.j1; ++j) {
+        const Sample s = ray_point(r, g, j);
+        const Taps t = make_taps(s, g);
+        if (t.okmask == 0u) continue;
+        const float *b = V + t.base;
+        float val[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const int64_t off = (c & 1) + ((c >> 1) & 1) * sy + (c >> 2) * sz;
+            val[c] = (t.okmask >> c) & 1u ? __ldg(b + off) : 0.0f;
+        }
+        float o = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            if ((t.okmask >> c) & 1u) o = add_rn(o, mul_rn(val[c], t.wt[c]));   // ATen: out += val*w, no fma
+        acc = add_rn(acc, o);                                                   // sum over the ray (sdct:81)
+    }
+    float o = mul_rn(acc, r.dx);                                                // * dx (sdct:81)
+    if (g.out_scale != 1.0f) o = mul_rn(o, g.out_scale);                        // *= 0.1 (sdct:85)
+    proj[((int64_t)(g.view0 + blockIdx.z) * g.rd + u) * g.rh + v] = o;
+}
+
+// Adjoint wrt the volume: every sample scatters (go*out_scale*dx) * w_tap into its 8 taps (RED.ADD.F32).
+__global__ void __launch_bounds__(32 * DRR_ROWS)
+    drr_backward_kernel(const float *__restrict__ gproj, float *__restrict__ gvol, DrrDims g, DrrViews views) {
+    const int v = blockIdx.x * 32 + threadIdx.x;
+    const int u = blockIdx.y * DRR_ROWS + threadIdx.y;
+    if (v >= g.rh || u >= g.rd) return;
+    const DrrView vw = views.v[blockIdx.z];
+    const Ray r = ray_setup(vw, g, u, v);
+    float *V = gvol + (int64_t)vw.vol * g.nvox;
+    const int64_t sy = g.h, sz = (int64_t)g.w * g.h;
+    float go = gproj[((int64_t)(g.view0 + blockIdx.z) * g.rd + u) * g.rh + v];
+    if (g.out_scale != 1.0f) go = mul_rn(go, g.out_scale);
+    const float gs = mul_rn(go, r.dx);
+    if (gs == 0.0f) return;
+    for (int j = r.j0; j <= r.j1; ++j) {
+        const Sample s = ray_point(r, g, j);
+        const Taps t = make_taps(s, g);
+        if (t.okmask == 0u) continue;
+        float *b = V + t.base;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const int64_t off = (c & 1) + ((c >> 1) & 1) * sy + (c >> 2) * sz;
+            if ((t.okmask >> c) & 1u) red_add(b + off, mul_rn(t.wt[c], gs));
+        }
+    }
+}
+
+// sdct:15-57 materialised, for API parity / bit-exactness checks only.
+__global__ void __launch_bounds__(32 * DRR_ROWS)
+    project_grid_kernel(float *__restrict__ grid, float *__restrict__ dx, DrrDims g, DrrViews views, int flip) {
+    const int v = blockIdx.x * 32 + threadIdx.x;
+    const int u = blockIdx.y * DRR_ROWS + threadIdx.y;
+    if (v >= g.rh || u >= g.rd) return;
+    const DrrView vw = views.v[blockIdx.z];
+    const Ray r = ray_setup(vw, g, u, v);
+    const int64_t ray = ((int64_t)(g.view0 + blockIdx.z) * g.rd + u) * g.rh + v;
+    if (dx) dx[ray] = r.dx;
+    if (!grid) return;
+    for (int j = 0; j < g.w; ++j) {
+        const float T = mul_rn(r.r2, sub_rn((float)j, r.sy));
+        const float X = add_rn(mul_rn(r.Dx, T), r.sx), Y = add_rn(mul_rn(r.Dy, T), r.sy), Z = add_rn(mul_rn(r.Dz, T), r.sz);
+        const float g0 = div_const(X, g.div_x), g1 = add_rn(div_const(Y, g.div_y), -1.0f), g2 = div_const(Z, g.div_z);
+        float *o = grid + (ray * g.w + j) * 3;
+        o[0] = flip ? g2 : g0; o[1] = g1; o[2] = flip ? g0 : g2;
+    }
+}
+
+static int fill_dims(DrrDims &g, int B, int d, int w, int h, int n_pose_sets, int P, int rd, int rh,
+                     const float spacing[3], int y_norm_mode, float out_scale) {
+    LR_REQUIRE(B > 0 && d > 0 && w > 1 && h > 0 && P > 0 && rd > 0 && rh > 0,
+               "drr: bad dimension (B=%d d=%d w=%d h=%d P=%d rd=%d rh=%d; w must be >= 2)", B, d, w, h, P, rd, rh);
+    LR_REQUIRE(n_pose_sets == 1 || n_pose_sets == B, "drr: n_pose_sets must be 1 or B (got %d, B=%d)", n_pose_sets, B);
+    LR_REQUIRE(y_norm_mode == LR_YNORM_WM1 || y_norm_mode == LR_YNORM_W, "drr: y_norm_mode must be 0 or 1");
+    LR_REQUIRE(spacing != nullptr, "drr: spacing is null");
+    LR_REQUIRE((rd + DRR_ROWS - 1) / DRR_ROWS <= 65535, "drr: detector too tall for the launch grid");
+    g.d = d; g.w = w; g.h = h; g.rd = rd; g.rh = rh; g.view0 = 0;
+    g.half_rd = (float)((double)rd / 2.0); g.half_rh = (float)((double)rh / 2.0);
+    g.sp0 = spacing[0]; g.sp1 = spacing[1]; g.sp2 = spacing[2];
+    g.div_x = make_const_div((float)((double)d / 2.0));
+    g.div_y = make_const_div(y_norm_mode == LR_YNORM_WM1 ? (float)(((double)w - 1.0) / 2.0) : (float)((double)w / 2.0));
+    g.div_z = make_const_div((float)((double)h / 2.0));
+    g.hd = (float)(d - 1) / 2.0f; g.hw = (float)(w - 1) / 2.0f; g.hh = (float)(h - 1) / 2.0f;
+    // |X| < d/2 + d/(d-1) is where a tap can be inside; +2 voxels of slack.  A single-plane axis (size 1) maps every
+    // coordinate to index 0, so it is never clipped.
+    g.lim_x = d > 1 ? (float)d / 2.0f + 2.0f + (float)d / (float)(d - 1) : 3.0e38f;
+    g.lim_z = h > 1 ? (float)h / 2.0f + 2.0f + (float)h / (float)(h - 1) : 3.0e38f;
+    g.out_scale = out_scale;
+    g.nvox = (int64_t)d * w * h;
+    return LR_OK;
+}
+
+// Calls launch(n_views_in_chunk, DrrViews, view0) for chunks of the (b,p) list.
+template <typename F>
+static int for_each_view_chunk(const double *poses, int n_pose_sets, int B, int P, F launch) {
+    const int total = B * P;
+    for (int v0 = 0; v0 < total; v0 += DRR_MAX_VIEWS) {
+        const int n = total - v0 < DRR_MAX_VIEWS ? total - v0 : DRR_MAX_VIEWS;
+        DrrViews vs;
+        for (int q = 0; q < n; ++q) {
+            const int b = (v0 + q) / P, p = (v0 + q) % P;
+            const double *ps = poses + ((size_t)(n_pose_sets == 1 ? 0 : b) * P + p) * 3;
+            vs.v[q].sx = (float)ps[0]; vs.v[q].sy = (float)ps[1]; vs.v[q].sz = (float)ps[2];   // sdct:28 .type(float32)
+            vs.v[q].vol = b;
+        }
+        if (int e = launch(n, vs, v0)) return e;
+    }
+    return LR_OK;
+}
+
+}  // namespace lr
+
+using namespace lr;
+
+extern "C" int lr_drr_forward(const float *vol, int B, int d, int w, int h, const double *poses, int n_pose_sets, int P,
+                              int rd, int rh, const float spacing[3], int y_norm_mode, float out_scale, float *proj,
+                              lr_stream_t stream) {
+    LR_REQUIRE(vol && poses && proj, "drr_forward: null pointer");
+    DrrDims g;
+    if (int e = fill_dims(g, B, d, w, h, n_pose_sets, P, rd, rh, spacing, y_norm_mode, out_scale)) return e;
+    return for_each_view_chunk(poses, n_pose_sets, B, P, [&](int n, const DrrViews &vs, int v0) {
+        g.view0 = v0;
+        dim3 grid((unsigned)((rh + 31) / 32), (unsigned)((rd + DRR_ROWS - 1) / DRR_ROWS), (unsigned)n);
+        drr_forward_kernel<<<grid, dim3(32, DRR_ROWS), 0, as_stream(stream)>>>(vol, proj, g, vs);
+        return check_launch("drr_forward_kernel");
+    });
+}
+
+extern "C" int lr_drr_backward(const float *grad_proj, int B, int d, int w, int h, const double *poses, int n_pose_sets,
+                               int P, int rd, int rh, const float spacing[3], int y_norm_mode, float out_scale,
+                               float *grad_vol, lr_stream_t stream) {
+    LR_REQUIRE(grad_proj && poses && grad_vol, "drr_backward: null pointer");
+    DrrDims g;
+    if (int e = fill_dims(g, B, d, w, h, n_pose_sets, P, rd, rh, spacing, y_norm_mode, out_scale)) return e;
+    return for_each_view_chunk(poses, n_pose_sets, B, P, [&](int n, const DrrViews &vs, int v0) {
+        g.view0 = v0;
+        dim3 grid((unsigned)((rh + 31) / 32), (unsigned)((rd + DRR_ROWS - 1) / DRR_ROWS), (unsigned)n);
+        drr_backward_kernel<<<grid, dim3(32, DRR_ROWS), 0, as_stream(stream)>>>(grad_proj, grad_vol, g, vs);
+        return check_launch("drr_backward_kernel");
+    });
+}
+
+extern "C" int lr_project_grid(const double *poses, int P, int rd, int rh, int d, int w, int h, const float spacing[3],
+                               int y_norm_mode, int flip, float *grid, float *dx, lr_stream_t stream) {
+    LR_REQUIRE(poses && (grid || dx), "project_grid: null pointer");
+    DrrDims g;
+    if (int e = fill_dims(g, 1, d, w, h, 1, P, rd, rh, spacing, y_norm_mode, 1.0f)) return e;
+    return for_each_view_chunk(poses, 1, 1, P, [&](int n, const DrrViews &vs, int v0) {
+        g.view0 = v0;
+        dim3 grid_dim((unsigned)((rh + 31) / 32), (unsigned)((rd + DRR_ROWS - 1) / DRR_ROWS), (unsigned)n);
+        project_grid_kernel<<<grid_dim, dim3(32, DRR_ROWS), 0, as_stream(stream)>>>(grid, dx, g, vs, flip);
+        return check_launch("project_grid_kernel");
+    });
+}

@@ -1,0 +1,310 @@
+// Displacement-field warp (spatial transformer), forward and adjoint, for sm_100a.
+//
+// Replaces reference src/liftreg/utils/net_utils.py:26-56 (Bilinear.forward / forward_stn), i.e. the
+// five-kernel sequence  (x+1)/2 -> zeros_like + 3 channel copies -> grid_sample_3d -> *2-1  (SURVEY.md §8 a9),
+// plus, optionally, the `disp + identity_map` add of LiftRegDeformSubspaceBackproj.py:68.
+//
+// One thread per output voxel along W (coalesced phi reads / out writes, 128 B per warp); the 8 taps are a
+// local gather served by L1/L2.  Arithmetic follows ATen's CPU grid_sampler_3d exactly: unnormalise
+// ((g+1)/2)*(S-1), weights (x1-x)*(y1-y)*(z1-z) left to right, taps accumulated in the order
+// tnw,tne,tsw,tse,bnw,bne,bsw,bse with separately rounded multiply and add.
+#include "common.cuh"
+
+namespace lr {
+
+struct WarpDims {
+    int C, D, H, W;
+    int64_t nvox;        // D*H*W
+    float hx, hy, hz;    // (W-1)/2, (H-1)/2, (D-1)/2
+    float mx, my, mz;    // W-1, H-1, D-1
+    double sp0, sp1, sp2;  // 1/(D-1), 1/(H-1), 1/(W-1) as float64 (identity map, net_utils.py:81)
+};
+
+// ATen grid_sampler_unnormalize(align_corners) then optional clip_coordinates.
+template <int PAD>
+__device__ __forceinline__ float source_index(float g, float half_sm1, float sm1) {
+    // ((g+1)/2)*(S-1) == RN(RN(g+1) * ((S-1)/2)): /2 is exact and (S-1)/2 is representable.
+    float i = mul_rn(add_rn(g, 1.0f), half_sm1);
+    if (PAD == LR_PAD_BORDER) i = fminf(sm1, fmaxf(i, 0.0f));
+    return i;
+}
+
+// net_utils.py:81-85 with numpy>=2 casting: fp32(float64(idx)*spacing) * 2 - 1
+__device__ __forceinline__ float identity_coord(int idx, double spacing) {
+    float v = __double2float_rn((double)idx * spacing);
+    return sub_rn(mul_rn(v, 2.0f), 1.0f);
+}
+
+template <bool IDENT>
+__device__ __forceinline__ void load_phi(const float *__restrict__ phi_b, const WarpDims &g, int64_t vox, int z, int y,
+                                         int x, float &gx, float &gy, float &gz) {
+    // channel c of phi addresses volume axis c; grid_sample's x is the last axis (net_utils.py:27-30)
+    gz = ld_stream(phi_b + vox);
+    gy = ld_stream(phi_b + g.nvox + vox);
+    gx = ld_stream(phi_b + 2 * g.nvox + vox);
+    if (IDENT) {  // LiftRegDeformSubspaceBackproj.py:68  deform_field = disp_field + id_transform
+        gz = add_rn(gz, identity_coord(z, g.sp0));
+        gy = add_rn(gy, identity_coord(y, g.sp1));
+        gx = add_rn(gx, identity_coord(x, g.sp2));
+    }
+}
+
+template <int PAD, int MODE, bool SCALE, bool IDENT>
+__global__ void __launch_bounds__(256) warp_forward_kernel(const float *__restrict__ img, const float *__restrict__ phi,
+                                                           float *__restrict__ out, WarpDims g) {
+    const int plane = blockIdx.x * blockDim.x + threadIdx.x;  // index inside the (H,W) plane
+    if (plane >= g.H * g.W) return;
+    const int z = blockIdx.y, b = blockIdx.z;
+    const int y = plane / g.W, x = plane - y * g.W;
+    const int64_t vox = (int64_t)z * g.H * g.W + plane;
+
+    float gx, gy, gz;
+    load_phi<IDENT>(phi + (int64_t)b * 3 * g.nvox, g, vox, z, y, x, gx, gy, gz);
+    const float ix = source_index<PAD>(gx, g.hx, g.mx);
+    const float iy = source_index<PAD>(gy, g.hy, g.my);
+    const float iz = source_index<PAD>(gz, g.hz, g.mz);
+
+    const float *src = img + (int64_t)b * g.C * g.nvox;
+    float *dst = out + (int64_t)b * g.C * g.nvox + vox;
+
+    if (MODE == LR_MODE_NEAREST) {
+        const int xn = __float2int_rn(ix), yn = __float2int_rn(iy), zn = __float2int_rn(iz);  // nearbyint: half to even
+        const bool ok = (unsigned)xn < (unsigned)g.W && (unsigned)yn < (unsigned)g.H && (unsigned)zn < (unsigned)g.D;
+        const int64_t off = ((int64_t)zn * g.H + yn) * g.W + xn;
+        for (int c = 0; c < g.C; ++c) {
+            float v = 0.0f;
+            if (ok) {
+                v = __ldg(src + c * g.nvox + off);
+                if (SCALE) v = mul_rn(add_rn(v, 1.0f), 0.5f);
+            }
+            if (SCALE) v = sub_rn(mul_rn(v, 2.0f), 1.0f);
+            st_stream(dst + c * g.nvox, v);
+        }
+        return;
+    }
+
+    const float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
+    const int x0 = __float2int_rd(ix), y0 = __float2int_rd(iy), z0 = __float2int_rd(iz);
+    const float wx1 = sub_rn(ix, fx), wx0 = sub_rn(add_rn(fx, 1.0f), ix);
+    const float wy1 = sub_rn(iy, fy), wy0 = sub_rn(add_rn(fy, 1.0f), iy);
+    const float wz1 = sub_rn(iz, fz), wz0 = sub_rn(add_rn(fz, 1.0f), iz);
+    const float a00 = mul_rn(wx0, wy0), a10 = mul_rn(wx1, wy0), a01 = mul_rn(wx0, wy1), a11 = mul_rn(wx1, wy1);
+    const float wt[8] = {mul_rn(a00, wz0), mul_rn(a10, wz0), mul_rn(a01, wz0), mul_rn(a11, wz0),
+                         mul_rn(a00, wz1), mul_rn(a10, wz1), mul_rn(a01, wz1), mul_rn(a11, wz1)};
+    const bool vx0 = (unsigned)x0 < (unsigned)g.W, vx1 = (unsigned)(x0 + 1) < (unsigned)g.W;
+    const bool vy0 = (unsigned)y0 < (unsigned)g.H, vy1 = (unsigned)(y0 + 1) < (unsigned)g.H;
+    const bool vz0 = (unsigned)z0 < (unsigned)g.D, vz1 = (unsigned)(z0 + 1) < (unsigned)g.D;
+    const bool ok[8] = {vx0 && vy0 && vz0, vx1 && vy0 && vz0, vx0 && vy1 && vz0, vx1 && vy1 && vz0,
+                        vx0 && vy0 && vz1, vx1 && vy0 && vz1, vx0 && vy1 && vz1, vx1 && vy1 && vz1};
+    const int64_t base = ((int64_t)z0 * g.H + y0) * g.W + x0;
+    const int64_t sy = g.W, sz = (int64_t)g.H * g.W;
+    const int64_t off[8] = {base, base + 1, base + sy, base + sy + 1, base + sz, base + sz + 1, base + sz + sy,
+                            base + sz + sy + 1};
+
+    for (int c = 0; c < g.C; ++c) {
+        const float *s = src + c * g.nvox;
+        float v[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v[t] = ok[t] ? __ldg(s + off[t]) : 0.0f;
+        float acc = 0.0f;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            if (ok[t]) {  // ATen skips out-of-bounds taps; in-bounds taps are  out += val * w  (no fma)
+                float val = v[t];
+                if (SCALE) val = mul_rn(add_rn(val, 1.0f), 0.5f);  // net_utils.py:50 (img+1)/2, fused per tap
+                acc = add_rn(acc, mul_rn(val, wt[t]));
+            }
+        }
+        if (SCALE) acc = sub_rn(mul_rn(acc, 2.0f), 1.0f);  // net_utils.py:52
+        st_stream(dst + c * g.nvox, acc);
+    }
+}
+
+// Adjoint.  grad_phi is a per-voxel gather (no atomics); grad_img is a scatter (RED.ADD.F32).
+// Follows ATen grid_sampler_3d_backward: gix -= tnw_val*(y1-y)*(z1-z)*gOut ... ; grad_grid = (S-1)/2 * gi,
+// zeroed where a border-clipped coordinate is outside (clip_coordinates_set_grad).
+template <int PAD, bool SCALE, bool IDENT>
+__global__ void __launch_bounds__(256)
+    warp_backward_kernel(const float *__restrict__ gout, const float *__restrict__ img, const float *__restrict__ phi,
+                         float *__restrict__ gimg, float *__restrict__ gphi, WarpDims g) {
+    const int plane = blockIdx.x * blockDim.x + threadIdx.x;
+    if (plane >= g.H * g.W) return;
+    const int z = blockIdx.y, b = blockIdx.z;
+    const int y = plane / g.W, x = plane - y * g.W;
+    const int64_t vox = (int64_t)z * g.H * g.W + plane;
+
+    float gx, gy, gz;
+    load_phi<IDENT>(phi + (int64_t)b * 3 * g.nvox, g, vox, z, y, x, gx, gy, gz);
+    float ix = mul_rn(add_rn(gx, 1.0f), g.hx), iy = mul_rn(add_rn(gy, 1.0f), g.hy), iz = mul_rn(add_rn(gz, 1.0f), g.hz);
+    float mx = g.hx, my = g.hy, mz = g.hz;
+    if (PAD == LR_PAD_BORDER) {
+        if (ix <= 0.0f) { ix = 0.0f; mx = 0.0f; } else if (ix >= g.mx) { ix = g.mx; mx = 0.0f; }
+        if (iy <= 0.0f) { iy = 0.0f; my = 0.0f; } else if (iy >= g.my) { iy = g.my; my = 0.0f; }
+        if (iz <= 0.0f) { iz = 0.0f; mz = 0.0f; } else if (iz >= g.mz) { iz = g.mz; mz = 0.0f; }
+    }
+    const float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
+    const int x0 = __float2int_rd(ix), y0 = __float2int_rd(iy), z0 = __float2int_rd(iz);
+    const float wx[2] = {sub_rn(add_rn(fx, 1.0f), ix), sub_rn(ix, fx)};
+    const float wy[2] = {sub_rn(add_rn(fy, 1.0f), iy), sub_rn(iy, fy)};
+    const float wz[2] = {sub_rn(add_rn(fz, 1.0f), iz), sub_rn(iz, fz)};
+    const int64_t base = ((int64_t)z0 * g.H + y0) * g.W + x0;
+
+    float gix = 0.0f, giy = 0.0f, giz = 0.0f;
+    for (int c = 0; c < g.C; ++c) {
+        const int64_t chan = ((int64_t)b * g.C + c) * g.nvox;
+        float go = ld_stream(gout + chan + vox);
+        if (SCALE) go = mul_rn(go, 2.0f);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const int tx = t & 1, ty = (t >> 1) & 1, tz = t >> 2;
+            const bool ok = (unsigned)(x0 + tx) < (unsigned)g.W && (unsigned)(y0 + ty) < (unsigned)g.H &&
+                            (unsigned)(z0 + tz) < (unsigned)g.D;
+            if (!ok) continue;
+            const int64_t o = chan + base + tx + (int64_t)ty * g.W + (int64_t)tz * g.H * g.W;
+            if (gimg) {
+                float wv = mul_rn(mul_rn(mul_rn(wx[tx], wy[ty]), wz[tz]), go);
+                red_add(gimg + o, SCALE ? mul_rn(wv, 0.5f) : wv);
+            }
+            if (gphi) {
+                float val = __ldg(img + o);
+                if (SCALE) val = mul_rn(add_rn(val, 1.0f), 0.5f);
+                const float tx_ = mul_rn(mul_rn(mul_rn(val, wy[ty]), wz[tz]), go);
+                const float ty_ = mul_rn(mul_rn(mul_rn(val, wx[tx]), wz[tz]), go);
+                const float tz_ = mul_rn(mul_rn(mul_rn(val, wx[tx]), wy[ty]), go);
+                gix = tx ? add_rn(gix, tx_) : sub_rn(gix, tx_);
+                giy = ty ? add_rn(giy, ty_) : sub_rn(giy, ty_);
+                giz = tz ? add_rn(giz, tz_) : sub_rn(giz, tz_);
+            }
+        }
+    }
+    if (gphi) {
+        float *gp = gphi + (int64_t)b * 3 * g.nvox + vox;
+        st_stream(gp, mul_rn(mz, giz));
+        st_stream(gp + g.nvox, mul_rn(my, giy));
+        st_stream(gp + 2 * g.nvox, mul_rn(mx, gix));
+    }
+}
+
+__global__ void identity_map_kernel(float *__restrict__ out, WarpDims g) {
+    const int plane = blockIdx.x * blockDim.x + threadIdx.x;
+    if (plane >= g.H * g.W) return;
+    const int z = blockIdx.y;
+    const int y = plane / g.W, x = plane - y * g.W;
+    const int64_t vox = (int64_t)z * g.H * g.W + plane;
+    out[vox] = identity_coord(z, g.sp0);
+    out[g.nvox + vox] = identity_coord(y, g.sp1);
+    out[2 * g.nvox + vox] = identity_coord(x, g.sp2);
+}
+
+__global__ void atten_coef_kernel(const float *__restrict__ hu, float *__restrict__ mu, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float v = fmaxf(hu[i], -1000.0f);                                     // sdct:8
+        mu[i] = mul_rn(div_rn(add_rn(v, 1000.0f), 1000.0f), 0.2f);            // sdct:9
+    }
+}
+
+static WarpDims make_dims(int C, int D, int H, int W) {
+    WarpDims g;
+    g.C = C; g.D = D; g.H = H; g.W = W;
+    g.nvox = (int64_t)D * H * W;
+    g.hx = (float)(W - 1) / 2.0f; g.hy = (float)(H - 1) / 2.0f; g.hz = (float)(D - 1) / 2.0f;
+    g.mx = (float)(W - 1); g.my = (float)(H - 1); g.mz = (float)(D - 1);
+    g.sp0 = 1.0 / (double)(D - 1); g.sp1 = 1.0 / (double)(H - 1); g.sp2 = 1.0 / (double)(W - 1);
+    return g;
+}
+
+static int check_warp_args(int B, int C, int D, int H, int W, int padding, int mode) {
+    LR_REQUIRE(B > 0 && C > 0 && D > 0 && H > 0 && W > 0, "warp: non-positive dimension (B=%d C=%d D=%d H=%d W=%d)", B, C, D, H, W);
+    LR_REQUIRE(B <= 65535 && D <= 65535, "warp: B and D must be <= 65535 (grid limits)");
+    LR_REQUIRE((int64_t)H * W < (1ll << 31), "warp: H*W too large");
+    LR_REQUIRE(padding == LR_PAD_ZEROS || padding == LR_PAD_BORDER, "warp: padding must be 0 (zeros) or 1 (border)");
+    LR_REQUIRE(mode == LR_MODE_LINEAR || mode == LR_MODE_NEAREST, "warp: mode must be 0 (linear) or 1 (nearest)");
+    return LR_OK;
+}
+
+template <int PAD, int MODE>
+static void launch_fwd(bool scale, bool ident, dim3 grid, cudaStream_t st, const float *img, const float *phi, float *out,
+                       const WarpDims &g) {
+    if (scale) {
+        if (ident) warp_forward_kernel<PAD, MODE, true, true><<<grid, 256, 0, st>>>(img, phi, out, g);
+        else warp_forward_kernel<PAD, MODE, true, false><<<grid, 256, 0, st>>>(img, phi, out, g);
+    } else {
+        if (ident) warp_forward_kernel<PAD, MODE, false, true><<<grid, 256, 0, st>>>(img, phi, out, g);
+        else warp_forward_kernel<PAD, MODE, false, false><<<grid, 256, 0, st>>>(img, phi, out, g);
+    }
+}
+
+template <int PAD>
+static void launch_bwd(bool scale, bool ident, dim3 grid, cudaStream_t st, const float *gout, const float *img,
+                       const float *phi, float *gimg, float *gphi, const WarpDims &g) {
+    if (scale) {
+        if (ident) warp_backward_kernel<PAD, true, true><<<grid, 256, 0, st>>>(gout, img, phi, gimg, gphi, g);
+        else warp_backward_kernel<PAD, true, false><<<grid, 256, 0, st>>>(gout, img, phi, gimg, gphi, g);
+    } else {
+        if (ident) warp_backward_kernel<PAD, false, true><<<grid, 256, 0, st>>>(gout, img, phi, gimg, gphi, g);
+        else warp_backward_kernel<PAD, false, false><<<grid, 256, 0, st>>>(gout, img, phi, gimg, gphi, g);
+    }
+}
+
+}  // namespace lr
+
+using namespace lr;
+
+extern "C" int lr_warp_forward(const float *img, const float *phi, int B, int C, int D, int H, int W, int padding,
+                               int mode, int using_scale, int disp_plus_identity, float *out, lr_stream_t stream) {
+    LR_REQUIRE(img && phi && out, "warp_forward: null pointer");
+    if (int e = check_warp_args(B, C, D, H, W, padding, mode)) return e;
+    WarpDims g = make_dims(C, D, H, W);
+    dim3 grid((unsigned)((H * W + 255) / 256), (unsigned)D, (unsigned)B);
+    cudaStream_t st = as_stream(stream);
+    const bool sc = using_scale != 0, id = disp_plus_identity != 0;
+    if (padding == LR_PAD_ZEROS) {
+        if (mode == LR_MODE_LINEAR) launch_fwd<LR_PAD_ZEROS, LR_MODE_LINEAR>(sc, id, grid, st, img, phi, out, g);
+        else launch_fwd<LR_PAD_ZEROS, LR_MODE_NEAREST>(sc, id, grid, st, img, phi, out, g);
+    } else {
+        if (mode == LR_MODE_LINEAR) launch_fwd<LR_PAD_BORDER, LR_MODE_LINEAR>(sc, id, grid, st, img, phi, out, g);
+        else launch_fwd<LR_PAD_BORDER, LR_MODE_NEAREST>(sc, id, grid, st, img, phi, out, g);
+    }
+    return check_launch("warp_forward_kernel");
+}
+
+extern "C" int lr_warp_backward(const float *grad_out, const float *img, const float *phi, int B, int C, int D, int H,
+                                int W, int padding, int mode, int using_scale, int disp_plus_identity, float *grad_img,
+                                float *grad_phi, lr_stream_t stream) {
+    LR_REQUIRE(grad_out && img && phi, "warp_backward: null pointer");
+    if (int e = check_warp_args(B, C, D, H, W, padding, mode)) return e;
+    if (!grad_img && !grad_phi) return LR_OK;
+    cudaStream_t st = as_stream(stream);
+    WarpDims g = make_dims(C, D, H, W);
+    if (mode == LR_MODE_NEAREST) {
+        // nearest sampling is piecewise constant in phi: zero grid gradient (ATen does the same); the image
+        // gradient is a pure scatter, which the linear kernel cannot express -> not needed by the reference
+        // (evaluate_dir_lab.py:221 warps label maps without autograd).
+        LR_REQUIRE(!grad_img, "warp_backward: grad_img is not supported for nearest mode");
+        cudaError_t ce = cudaMemsetAsync(grad_phi, 0, sizeof(float) * 3 * (size_t)B * g.nvox, st);
+        if (ce != cudaSuccess) { set_error("warp_backward: memset failed: %s", cudaGetErrorString(ce)); return LR_ERR_CUDA; }
+        return LR_OK;
+    }
+    dim3 grid((unsigned)((H * W + 255) / 256), (unsigned)D, (unsigned)B);
+    const bool sc = using_scale != 0, id = disp_plus_identity != 0;
+    if (padding == LR_PAD_ZEROS) launch_bwd<LR_PAD_ZEROS>(sc, id, grid, st, grad_out, img, phi, grad_img, grad_phi, g);
+    else launch_bwd<LR_PAD_BORDER>(sc, id, grid, st, grad_out, img, phi, grad_img, grad_phi, g);
+    return check_launch("warp_backward_kernel");
+}
+
+extern "C" int lr_identity_map(int D, int H, int W, float *out, lr_stream_t stream) {
+    LR_REQUIRE(out, "identity_map: null pointer");
+    LR_REQUIRE(D > 1 && H > 1 && W > 1 && D <= 65535, "identity_map: each size must be in [2, 65535]");
+    WarpDims g = make_dims(1, D, H, W);
+    dim3 grid((unsigned)((H * W + 255) / 256), (unsigned)D, 1);
+    identity_map_kernel<<<grid, 256, 0, as_stream(stream)>>>(out, g);
+    return check_launch("identity_map_kernel");
+}
+
+extern "C" int lr_atten_coef(const float *hu, int64_t n, float *mu, lr_stream_t stream) {
+    LR_REQUIRE(hu && mu && n >= 0, "atten_coef: bad argument");
+    if (n == 0) return LR_OK;
+    int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+    atten_coef_kernel<<<blocks, 256, 0, as_stream(stream)>>>(hu, mu, n);
+    return check_launch("atten_coef_kernel");
+}

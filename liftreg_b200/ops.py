@@ -1,0 +1,277 @@
+"""Functional PyTorch surface over the C-ABI: tensors in, tensors out, autograd wired.
+
+PyTorch is plumbing here (device memory, streams, autograd graph); all arithmetic happens in
+libliftreg_b200.so.  CUDA float32 tensors only -- there is no CPU fallback.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _native
+
+PAD_ZEROS, PAD_BORDER = 0, 1
+MODE_LINEAR, MODE_NEAREST = 0, 1
+YNORM_WM1, YNORM_W = 0, 1
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _need_cuda_f32(t, name):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor, got %s" % (name, type(t).__name__))
+    if not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor: liftreg_b200 has no CPU path (got device %s)" % (name, t.device))
+    if t.dtype != torch.float32:
+        raise TypeError("%s must be float32 (got %s)" % (name, t.dtype))
+    return t.contiguous()
+
+
+def _poses64(poses):
+    """(P,3) or (n_sets,P,3) -> contiguous float64 numpy (n_sets,P,3)."""
+    if isinstance(poses, torch.Tensor):
+        poses = poses.detach().cpu().numpy()
+    a = np.ascontiguousarray(poses, dtype=np.float64)
+    if a.ndim == 2:
+        a = a[None]
+    if a.ndim != 3 or a.shape[2] != 3:
+        raise ValueError("poses must have shape (P,3) or (B,P,3), got %s" % (a.shape,))
+    return a
+
+
+def _poses32(poses):
+    if isinstance(poses, torch.Tensor):
+        poses = poses.detach().cpu().numpy()
+    a = np.ascontiguousarray(poses, dtype=np.float32)
+    if a.ndim == 3:
+        a = a[0]            # geometry frozen from batch item 0 (reference model :85-87)
+    if a.ndim != 2 or a.shape[1] != 3:
+        raise ValueError("poses must have shape (P,3) or (B,P,3), got %s" % (a.shape,))
+    return np.ascontiguousarray(a)
+
+
+def _spacing3(spacing):
+    if isinstance(spacing, torch.Tensor):
+        spacing = spacing.detach().cpu().numpy()
+    a = np.ascontiguousarray(np.asarray(spacing, dtype=np.float32).reshape(-1))
+    if a.size != 3:
+        raise ValueError("spacing must have 3 entries")
+    return a
+
+
+def _fp(a):
+    return a.ctypes.data_as(_native.c_float_p)
+
+
+def _dp(a):
+    return a.ctypes.data_as(_native.c_double_p)
+
+
+# --------------------------------------------------------------------------- DRR
+class _DRR(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, vol, poses, rd, rh, spacing, y_norm_mode, out_scale):
+        vol = _need_cuda_f32(vol, "vol")
+        B, d, w, h = vol.shape
+        n_sets, P, _ = poses.shape
+        proj = torch.empty((B, P, rd, rh), device=vol.device, dtype=torch.float32)
+        with torch.cuda.device(vol.device):
+            _native.check(_native.lib().lr_drr_forward(_ptr(vol), B, d, w, h, _dp(poses), n_sets, P, rd, rh,
+                                                       _fp(spacing), y_norm_mode, out_scale, _ptr(proj), _stream()),
+                          "lr_drr_forward")
+        ctx.geom = (poses, rd, rh, spacing, y_norm_mode, out_scale, (B, d, w, h))
+        return proj
+
+    @staticmethod
+    def backward(ctx, grad_proj):
+        poses, rd, rh, spacing, y_norm_mode, out_scale, (B, d, w, h) = ctx.geom
+        grad_proj = _need_cuda_f32(grad_proj, "grad_proj")
+        n_sets, P, _ = poses.shape
+        grad_vol = torch.zeros((B, d, w, h), device=grad_proj.device, dtype=torch.float32)
+        with torch.cuda.device(grad_proj.device):
+            _native.check(_native.lib().lr_drr_backward(_ptr(grad_proj), B, d, w, h, _dp(poses), n_sets, P, rd, rh,
+                                                        _fp(spacing), y_norm_mode, out_scale, _ptr(grad_vol), _stream()),
+                          "lr_drr_backward")
+        return grad_vol, None, None, None, None, None, None
+
+
+def drr_project(vol, poses, resolution, spacing, y_norm_mode=YNORM_WM1, out_scale=0.1):
+    """Cone-beam DRR of vol (B,d,w,h) -> (B,P,rd,rh); differentiable wrt vol.
+
+    Replaces reference sdct:59-86 (y_norm_mode=0, out_scale=0.1) and layers.py:182-187 (y_norm_mode=1, out_scale=1).
+    poses: (P,3) shared by the batch, or (B,P,3); float64, voxel units.
+    """
+    poses = _poses64(poses)
+    if vol.dim() != 4:
+        raise ValueError("vol must be (B,d,w,h), got %s" % (tuple(vol.shape),))
+    if poses.shape[0] not in (1, vol.shape[0]):
+        raise ValueError("poses batch (%d) must be 1 or B (%d)" % (poses.shape[0], vol.shape[0]))
+    rd, rh = int(resolution[0]), int(resolution[1])
+    return _DRR.apply(vol, poses, rd, rh, _spacing3(spacing), int(y_norm_mode), float(out_scale))
+
+
+def project_grid(poses, resolution, obj_shape, spacing, device, y_norm_mode=YNORM_WM1, flip=False, want_grid=True):
+    """Materialised sample grid (P,rd,rh,w,3) and dx (P,rd,rh) -- reference sdct:15-57, for API parity only."""
+    poses = _poses64(poses)[0]
+    P = poses.shape[0]
+    rd, rh = int(resolution[0]), int(resolution[1])
+    d, w, h = (int(s) for s in obj_shape)
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("project_grid needs a CUDA device: liftreg_b200 has no CPU path")
+    grid = torch.empty((P, rd, rh, w, 3), device=dev, dtype=torch.float32) if want_grid else None
+    dx = torch.empty((P, rd, rh), device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        _native.check(_native.lib().lr_project_grid(_dp(poses), P, rd, rh, d, w, h, _fp(_spacing3(spacing)),
+                                                    int(y_norm_mode), int(bool(flip)), _ptr(grid), _ptr(dx), _stream()),
+                      "lr_project_grid")
+    return grid, dx
+
+
+# --------------------------------------------------------------------------- backprojection
+class _Backproject(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, proj, poses, d, w, h, out, channel_offset):
+        proj = _need_cuda_f32(proj, "target_proj")
+        B, P, pw, ph = proj.shape
+        nv = d * w * h
+        if out is None:
+            out = torch.empty((B, P, d, w, h), device=proj.device, dtype=torch.float32)
+            view, bs, cs = out, P * nv, nv
+        else:
+            if not (out.is_cuda and out.dtype == torch.float32 and out.is_contiguous()):
+                raise ValueError("out must be a contiguous CUDA float32 tensor")
+            if out.dim() != 5 or out.shape[0] != B or tuple(out.shape[2:]) != (d, w, h) \
+                    or out.shape[1] < channel_offset + P:
+                raise ValueError("out must be (B,>=%d,%d,%d,%d), got %s" % (channel_offset + P, d, w, h, tuple(out.shape)))
+            view, bs, cs = out[:, channel_offset:channel_offset + P], out.shape[1] * nv, nv
+            ctx.mark_dirty(out)
+        with torch.cuda.device(proj.device):
+            _native.check(_native.lib().lr_backproject_forward(_ptr(proj), _fp(poses), B, P, pw, ph, d, w, h,
+                                                               ctypes.c_void_p(view.data_ptr()), bs, cs, _stream()),
+                          "lr_backproject_forward")
+        ctx.geom = (poses, B, P, pw, ph, d, w, h, channel_offset, out.shape[1])
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        poses, B, P, pw, ph, d, w, h, off, nchan = ctx.geom
+        grad_out = _need_cuda_f32(grad_out, "grad_out")
+        nv = d * w * h
+        gview = grad_out[:, off:off + P]
+        grad_proj = torch.zeros((B, P, pw, ph), device=grad_out.device, dtype=torch.float32)
+        with torch.cuda.device(grad_out.device):
+            _native.check(_native.lib().lr_backproject_backward(ctypes.c_void_p(gview.data_ptr()), nchan * nv, nv, _fp(poses),
+                                                                B, P, pw, ph, d, w, h, _ptr(grad_proj), _stream()),
+                          "lr_backproject_backward")
+        return grad_proj, None, None, None, None, None, None
+
+
+def backproject(target_proj, poses, img_shape, out=None, channel_offset=0):
+    """Lift projections (B,P,pw,ph) into a volume (B,P,d,w,h); differentiable wrt target_proj.
+
+    Replaces reference sdct:227-250 + LiftRegDeformSubspaceBackproj.py:85-93 in one kernel (no 131 MB grid).
+    poses: (P,3) or (B,P,3) float32 (item 0 is used, as the reference freezes geometry from the first batch).
+    out/channel_offset: optionally write into channels [offset, offset+P) of a pre-allocated (B,Ctot,d,w,h)
+    buffer, which removes the torch.cat of model :95-98; the whole buffer is returned.
+    """
+    if target_proj.dim() != 4:
+        raise ValueError("target_proj must be (B,P,pw,ph), got %s" % (tuple(target_proj.shape),))
+    poses = _poses32(poses)
+    if poses.shape[0] != target_proj.shape[1]:
+        raise ValueError("poses has %d views but target_proj has %d" % (poses.shape[0], target_proj.shape[1]))
+    d, w, h = (int(s) for s in img_shape)
+    return _Backproject.apply(target_proj, poses, d, w, h, out, int(channel_offset))
+
+
+def backproj_grid(poses, img_shape, proj_shape, device):
+    """Materialised voxel->detector grid (P,2,d,w,h) -- reference sdct:227-250, for API parity only."""
+    poses = _poses32(poses)
+    d, w, h = (int(s) for s in img_shape)
+    pw, ph = (int(s) for s in proj_shape)
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("backproj_grid needs a CUDA device: liftreg_b200 has no CPU path")
+    grid = torch.empty((poses.shape[0], 2, d, w, h), device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        _native.check(_native.lib().lr_backproj_grid(_fp(poses), poses.shape[0], d, w, h, pw, ph, _ptr(grid), _stream()),
+                      "lr_backproj_grid")
+    return grid
+
+
+# --------------------------------------------------------------------------- warp
+class _Warp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, phi, padding, mode, using_scale, disp_plus_identity):
+        img = _need_cuda_f32(img, "input1")
+        phi = _need_cuda_f32(phi, "input2")
+        B, C, D, H, W = img.shape
+        out = torch.empty_like(img)
+        with torch.cuda.device(img.device):
+            _native.check(_native.lib().lr_warp_forward(_ptr(img), _ptr(phi), B, C, D, H, W, padding, mode,
+                                                        int(using_scale), int(disp_plus_identity), _ptr(out), _stream()),
+                          "lr_warp_forward")
+        ctx.save_for_backward(img, phi)
+        ctx.cfg = (padding, mode, using_scale, disp_plus_identity)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        img, phi = ctx.saved_tensors
+        padding, mode, using_scale, ident = ctx.cfg
+        grad_out = _need_cuda_f32(grad_out, "grad_out")
+        B, C, D, H, W = img.shape
+        need_img, need_phi = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if need_img and mode == MODE_NEAREST:
+            raise NotImplementedError("gradient wrt the image is not implemented for nearest-mode warps")
+        gimg = torch.zeros_like(img) if need_img else None
+        gphi = torch.empty_like(phi) if need_phi else None
+        with torch.cuda.device(img.device):
+            _native.check(_native.lib().lr_warp_backward(_ptr(grad_out), _ptr(img), _ptr(phi), B, C, D, H, W, padding, mode,
+                                                         int(using_scale), int(ident), _ptr(gimg), _ptr(gphi), _stream()),
+                          "lr_warp_backward")
+        return gimg, gphi, None, None, None, None
+
+
+def warp(img, phi, zero_boundary=False, using_scale=True, mode="bilinear", disp_plus_identity=False):
+    """Spatial transformer: img (B,C,D,H,W) sampled at phi (B,3,D,H,W) in [-1,1]; differentiable wrt both.
+
+    Replaces reference net_utils.py:26-56.  disp_plus_identity=True treats phi as a displacement and adds the
+    identity map in-kernel (fuses LiftRegDeformSubspaceBackproj.py:68).
+    """
+    if mode not in ("bilinear", "nearest"):
+        raise ValueError("mode must be 'bilinear' or 'nearest', got %r" % (mode,))
+    if img.dim() != 5 or phi.dim() != 5 or phi.shape[1] != 3 or phi.shape[0] != img.shape[0] \
+            or tuple(phi.shape[2:]) != tuple(img.shape[2:]):
+        raise ValueError("expected input1 (B,C,D,H,W) and input2 (B,3,D,H,W); got %s and %s"
+                         % (tuple(img.shape), tuple(phi.shape)))
+    return _Warp.apply(img, phi, PAD_ZEROS if zero_boundary else PAD_BORDER,
+                       MODE_LINEAR if mode == "bilinear" else MODE_NEAREST, bool(using_scale), bool(disp_plus_identity))
+
+
+def identity_map(sz, device):
+    """Normalised identity map (3,*sz) on `device` -- reference net_utils.py:59-87."""
+    D, H, W = (int(s) for s in sz)
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("identity_map needs a CUDA device: liftreg_b200 has no CPU path")
+    out = torch.empty((3, D, H, W), device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        _native.check(_native.lib().lr_identity_map(D, H, W, _ptr(out), _stream()), "lr_identity_map")
+    return out
+
+
+def atten_coef_(img):
+    """In-place HU -> attenuation on a CUDA tensor -- reference sdct:11-13."""
+    t = _need_cuda_f32(img, "img")
+    if t.data_ptr() != img.data_ptr():
+        raise ValueError("atten_coef_ needs a contiguous tensor")
+    with torch.cuda.device(t.device):
+        _native.check(_native.lib().lr_atten_coef(_ptr(t), t.numel(), _ptr(t), _stream()), "lr_atten_coef")
+    return img

@@ -1,0 +1,402 @@
+"""GPU parity: the CUDA path (through the C-ABI) against the CPU oracle and the reference-generated goldens.
+
+Bars (BASELINE.json north_star): coordinates, indices and weights bit-exact; sampled outputs <= 1e-5 relative L2
+per image / per volume in fp32.  Where the op order is fully reproduced (warp, backprojection, DRR with the
+oracle's sequential ray sum) the comparison is exact equality.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5          # north-star tolerance, relative L2 per image / volume
+GRAD_TOL = 2e-5     # gradients: fp32 atomics reorder the scatter sums
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from liftreg_b200 import _native
+    assert _native.lib().lr_device_count() >= 1
+    return torch.device("cuda:0")
+
+
+def cu(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def per_image_rel_l2(a, b):
+    a = a.reshape(-1, a.shape[-2], a.shape[-1]); b = b.reshape(a.shape)
+    return max(rel_l2(x, y) for x, y in zip(a, b))
+
+
+# ------------------------------------------------------------------ ray geometry
+@pytest.mark.parametrize("name", ["ray_grid_even", "ray_grid_odd"])
+def test_project_grid_bit_exact_vs_reference_golden(dev, name):
+    from liftreg_b200 import sdct_projection_utils as sdct
+    g = load_golden(name)
+    grid, dx = sdct.project_grid_multi(g["poses"], g["resolution"], [1, 1, 1], g["obj_shape"],
+                                       torch.from_numpy(g["spacing"]), dev, torch.float32)
+    assert np.array_equal(grid.cpu().numpy(), g["grid"])
+    assert np.array_equal(dx.cpu().numpy(), g["dx"])
+
+
+def test_proj_layer_grid_bit_exact_vs_reference_golden(dev):
+    from liftreg_b200 import layers
+    g = load_golden("ray_grid_projlayer")
+    layer = layers.proj_layer(torch.from_numpy(g["spacing"]), 1.5, 40.0, 3, tuple(g["obj_shape"]), (8, 8), dev)
+    assert np.array_equal(layer.dx.cpu().numpy(), g["dx"])
+    assert np.array_equal(layer.grids.cpu().numpy(), g["grid_flipped"])
+
+
+def test_project_grid_vs_oracle_full_detector(dev):
+    """160^3 geometry, 240^2 detector, 1 view: every one of the 9.2 M sample coordinates bit-identical."""
+    from liftreg_b200 import ops, synthetic
+    from oracle import c_oracle
+    poses = synthetic.wrapper_poses(60.0, 4, 160)[1:2]
+    grid, dx = ops.project_grid(poses, (240, 240), (160, 160, 160), (2.2, 2.2, 2.2), dev)
+    og, odx = c_oracle.project_grid(poses, (240, 240), (160, 160, 160), (2.2, 2.2, 2.2))
+    assert np.array_equal(dx.cpu().numpy(), odx)
+    assert np.array_equal(grid.cpu().numpy(), og)
+
+
+# ------------------------------------------------------------------ DRR forward
+def test_drr_small_vs_golden_and_oracle(dev):
+    from liftreg_b200 import sdct_projection_utils as sdct
+    from oracle import c_oracle
+    g = load_golden("drr_small")
+    out = sdct.calculate_projection(g["vol"], g["poses"], g["resolution"], [1, 1, 1], tuple(g["spacing"]), dev)
+    assert out.shape == g["proj"].shape and out.dtype == np.float32
+    assert per_image_rel_l2(out, g["proj"]) <= TOL                       # reference (torch.sum cascade order)
+    ora = c_oracle.drr_forward(g["vol"], g["poses"], g["resolution"], g["spacing"])
+    assert np.array_equal(out, ora)                                      # same sequential fp32 ray sum: exact
+
+
+def test_drr_csv_poses_and_anisotropic_spacing(dev):
+    from liftreg_b200 import sdct_projection_utils as sdct
+    g = load_golden("drr_small_csvposes")
+    out = sdct.calculate_projection(g["vol"], g["poses"], g["resolution"], [1, 1, 1], tuple(g["spacing"]), dev)
+    assert per_image_rel_l2(out, g["proj"]) <= TOL
+
+
+def test_drr_cfg1_vs_reference_golden(dev):
+    """BASELINE configs[0]: 160^3, 4 views / 60 deg, 240^2 detector, against the reference's CPU output."""
+    from liftreg_b200 import sdct_projection_utils as sdct, synthetic
+    g = load_golden("drr_cfg1")
+    mu = synthetic.hu_to_mu(synthetic.ct_phantom((160, 160, 160)))
+    assert abs(mu.astype(np.float64).sum() - float(g["mu_sum64"])) <= 1e-6 * abs(float(g["mu_sum64"]))
+    proj, poses = sdct.calculate_projection_wraper(mu, 60.0, 4, (2.2, 2.2, 2.2))
+    assert np.array_equal(poses, g["poses"])
+    assert proj.shape == (4, 240, 240)
+    for p in range(4):
+        assert rel_l2(proj[p, ::6, ::6], g["proj_sub"][p]) <= TOL
+        assert rel_l2(proj[p, 120, :], g["proj_row"][p]) <= TOL
+    norms = np.sqrt((proj.astype(np.float64) ** 2).sum(axis=(1, 2)))
+    assert np.allclose(norms, g["per_view_norm"], rtol=TOL, atol=0)
+    assert abs(proj.astype(np.float64).sum() - float(g["sum64"])) <= TOL * abs(float(g["sum64"]))
+
+
+@pytest.mark.parametrize("shape,res,P", [((7, 9, 5), (11, 3), 1), ((33, 17, 65), (50, 97), 5), ((1, 4, 1), (3, 3), 2),
+                                         ((16, 2, 16), (40, 40), 3)])
+def test_drr_ragged_shapes_vs_oracle(dev, shape, res, P):
+    from liftreg_b200 import ops, synthetic
+    from oracle import c_oracle
+    rs = np.random.RandomState(1)
+    vol = rs.rand(2, *shape).astype(np.float32)
+    poses = synthetic.wrapper_poses(50.0, P, shape[1])
+    out = ops.drr_project(cu(vol, dev), poses, res, (2.0, 1.5, 3.0)).cpu().numpy()
+    ora = c_oracle.drr_forward(vol, poses, res, (2.0, 1.5, 3.0))
+    assert np.array_equal(out, ora)
+
+
+def test_drr_rays_that_miss_the_volume_are_exactly_zero(dev):
+    from liftreg_b200 import ops
+    vol = torch.ones((1, 8, 8, 8), device=dev)
+    poses = np.array([[0.0, 40.0, 0.0]])
+    out = ops.drr_project(vol, poses, (64, 64), (1.0, 1.0, 1.0)).cpu().numpy()
+    assert (out[0, 0, :8, :] == 0).all() and (out[0, 0, :, -8:] == 0).all()
+    assert out[0, 0, 32, 32] > 0
+
+
+def test_drr_per_item_poses_and_many_views(dev):
+    """(B,P,3) pose sets and more views than one launch chunk (128)."""
+    from liftreg_b200 import ops, synthetic
+    from oracle import c_oracle
+    rs = np.random.RandomState(4)
+    vol = rs.rand(2, 6, 10, 7).astype(np.float32)
+    poses = np.stack([synthetic.wrapper_poses(60.0, 70, 10), synthetic.wrapper_poses(40.0, 70, 10, 3.0)])
+    out = ops.drr_project(cu(vol, dev), poses, (9, 8), (1.0, 1.0, 1.0)).cpu().numpy()
+    for b in range(2):
+        assert np.array_equal(out[b], c_oracle.drr_forward(vol[b], poses[b], (9, 8), (1.0, 1.0, 1.0)))
+
+
+def test_drr_linearity_full_size(dev):
+    """Size-independent property at 160^3/240^2: DRR(a*V1 + V2) == a*DRR(V1) + DRR(V2) to fp32 round-off."""
+    from liftreg_b200 import ops, synthetic
+    rs = np.random.RandomState(8)
+    v1 = cu(synthetic.hu_to_mu(synthetic.ct_phantom((160, 160, 160)))[None], dev)
+    v2 = cu(rs.rand(1, 160, 160, 160).astype(np.float32) * 0.1, dev)
+    poses = synthetic.wrapper_poses(60.0, 4, 160)
+    f = lambda v: ops.drr_project(v, poses, (240, 240), (2.2, 2.2, 2.2))
+    lhs = f(0.5 * v1 + v2).cpu().numpy()
+    rhs = (0.5 * f(v1) + f(v2)).cpu().numpy()
+    assert per_image_rel_l2(lhs, rhs) <= TOL
+
+
+# ------------------------------------------------------------------ proj_layer + DRR backward
+def test_proj_layer_forward_backward_vs_reference_golden(dev):
+    from liftreg_b200 import layers
+    g = load_golden("proj_layer")
+    layer = layers.proj_layer(torch.from_numpy(g["spacing"]), float(g["resolution_scale"]), float(g["scan_range"]),
+                              int(g["proj_num"]), tuple(g["in_shape"]), tuple(int(s) for s in g["out_shape"]), dev)
+    x = cu(g["x"], dev).requires_grad_(True)
+    y = layer(x)
+    assert per_image_rel_l2(y.detach().cpu().numpy(), g["out"]) <= TOL
+    y.backward(cu(g["grad_out"], dev))
+    for b in range(x.shape[0]):
+        assert rel_l2(x.grad[b].cpu().numpy(), g["grad_x"][b]) <= GRAD_TOL
+
+
+def test_drr_backward_vs_oracle_and_adjoint_identity(dev):
+    from liftreg_b200 import ops, synthetic
+    from oracle import c_oracle
+    rs = np.random.RandomState(9)
+    shape, res = (14, 12, 18), (20, 26)
+    vol = rs.rand(1, *shape).astype(np.float32)
+    go = rs.randn(1, 3, *res).astype(np.float32)
+    poses = synthetic.wrapper_poses(60.0, 3, shape[1])
+    v = cu(vol, dev).requires_grad_(True)
+    y = ops.drr_project(v, poses, res, (2.2, 2.2, 2.2))
+    y.backward(cu(go, dev))
+    ora = c_oracle.drr_backward(go, shape, poses, (2.2, 2.2, 2.2))
+    assert rel_l2(v.grad.cpu().numpy(), ora) <= GRAD_TOL
+    # <DRR(v), g> == <v, DRR^T(g)>
+    lhs = float((y.detach().double() * cu(go, dev).double()).sum())
+    rhs = float((v.detach().double() * v.grad.double()).sum())
+    assert abs(lhs - rhs) <= 1e-5 * abs(lhs)
+
+
+# ------------------------------------------------------------------ backprojection
+def test_backproj_grid_bit_exact_vs_reference_golden(dev):
+    from liftreg_b200 import sdct_projection_utils as sdct
+    g = load_golden("backproj_small")
+    grid = sdct.backproj_grids_with_poses(g["poses"][0:1], g["img_shape"], g["proj_shape"], device=dev)
+    assert np.array_equal(grid.cpu().numpy(), g["grid"])
+
+
+def test_backproject_bit_exact_vs_reference_golden_and_grad(dev):
+    from liftreg_b200 import sdct_projection_utils as sdct
+    g = load_golden("backproj_small")
+    tp = cu(g["target_proj"], dev).requires_grad_(True)
+    out = sdct.backproject(tp, g["poses"], g["img_shape"])
+    assert np.array_equal(out.detach().cpu().numpy(), g["out"])
+    out.backward(cu(g["grad_out"], dev))
+    for b in range(tp.shape[0]):
+        for p in range(tp.shape[1]):
+            assert rel_l2(tp.grad[b, p].cpu().numpy(), g["grad_proj"][b, p]) <= GRAD_TOL
+
+
+def test_backproject_into_concat_buffer(dev):
+    """f1: write channels 1..P of the (B,1+P,d,w,h) encoder input directly (no torch.cat)."""
+    from liftreg_b200 import ops
+    g = load_golden("backproj_small")
+    B, P = g["target_proj"].shape[:2]
+    d, w, h = (int(s) for s in g["img_shape"])
+    buf = torch.full((B, 1 + P, d, w, h), 7.0, device=dev)
+    ret = ops.backproject(cu(g["target_proj"], dev), g["poses"], (d, w, h), out=buf, channel_offset=1)
+    assert ret.data_ptr() == buf.data_ptr()
+    assert (buf[:, 0] == 7.0).all()
+    assert np.array_equal(buf[:, 1:].cpu().numpy(), g["out"])
+
+
+def test_backproject_cfg2_vs_reference_golden(dev):
+    """BASELINE configs[1]: 4 x 256^2 -> 160^3, inputs = normalised DRRs of the phantom made by OUR DRR kernel."""
+    from liftreg_b200 import ops, synthetic, sdct_projection_utils as sdct
+    g = load_golden("backproj_cfg2")
+    mu = synthetic.hu_to_mu(synthetic.ct_phantom((160, 160, 160)))
+    poses = synthetic.wrapper_poses(60.0, 4, 160)
+    proj256 = sdct.calculate_projection(mu, poses, (256, 256), [1, 1, 1], (2.2, 2.2, 2.2), dev)
+    for p in range(4):
+        assert rel_l2(proj256[p, ::8, ::8], g["proj256_sub"][p]) <= TOL
+    tp = cu(synthetic.normalise_projection(proj256)[None], dev)
+    vol = ops.backproject(tp, poses.astype(np.float32), (160, 160, 160)).cpu().numpy()
+    for p in range(4):
+        assert rel_l2(vol[0, p, ::10, ::10, ::10], g["out_sub"][0, p]) <= TOL
+        assert rel_l2(vol[0, p, 80, 80, :], g["out_line"][p]) <= TOL
+    norms = np.sqrt((vol.astype(np.float64) ** 2).sum(axis=(0, 2, 3, 4)))
+    assert np.allclose(norms, g["per_view_norm"], rtol=TOL, atol=0)
+
+
+@pytest.mark.parametrize("shape,pshape,B,P", [((5, 7, 3), (9, 4), 1, 1), ((33, 6, 70), (40, 31), 3, 2),
+                                              ((40, 9, 300), (64, 350), 1, 2), ((2, 2, 2), (1, 1), 2, 66)])
+def test_backproject_ragged_shapes_vs_oracle(dev, shape, pshape, B, P):
+    from liftreg_b200 import ops, synthetic
+    from oracle import c_oracle
+    rs = np.random.RandomState(2)
+    tp = rs.uniform(-1, 1, (B, P) + pshape).astype(np.float32)
+    poses = synthetic.wrapper_poses(60.0, P, shape[1]).astype(np.float32)
+    out = ops.backproject(cu(tp, dev), poses, shape).cpu().numpy()
+    assert np.array_equal(out, c_oracle.backproject_forward(tp, poses, shape))
+
+
+def test_backproject_constant_image_property_full_size(dev):
+    """Size-independent property at 160^3: a constant detector image backprojects to that constant wherever all
+    four taps are inside the detector, and to [0, c] elsewhere (zeros padding)."""
+    from liftreg_b200 import ops, synthetic
+    poses = synthetic.wrapper_poses(60.0, 4, 160).astype(np.float32)
+    tp = torch.full((2, 4, 256, 256), 0.75, device=dev)
+    vol = ops.backproject(tp, poses, (160, 160, 160))
+    assert float(vol.max()) <= 0.75 + 1e-6 and float(vol.min()) >= 0.0
+    assert float((vol - 0.75).abs().lt(1e-6).float().mean()) > 0.9
+
+
+# ------------------------------------------------------------------ warp
+@pytest.mark.parametrize("zb", [False, True])
+@pytest.mark.parametrize("us", [False, True])
+@pytest.mark.parametrize("mode", ["bilinear", "nearest"])
+def test_warp_bit_exact_vs_reference_golden(dev, zb, us, mode):
+    from liftreg_b200 import net_utils
+    g = load_golden("warp_small")
+    key = "zb%d_us%d_%s" % (zb, us, mode)
+    img = cu(g["img"], dev).requires_grad_(mode == "bilinear")
+    phi = cu(g["phi"], dev).requires_grad_(True)
+    out = net_utils.Bilinear(zero_boundary=zb, using_scale=us, mode=mode)(img, phi)
+    assert np.array_equal(out.detach().cpu().numpy(), g["out_" + key])
+    if mode == "bilinear":
+        out.backward(cu(g["grad_out"], dev))
+        assert rel_l2(img.grad.cpu().numpy(), g["gimg_" + key]) <= GRAD_TOL
+        assert rel_l2(phi.grad.cpu().numpy(), g["gphi_" + key]) <= GRAD_TOL
+    else:
+        out.backward(cu(g["grad_out"], dev))
+        assert float(phi.grad.abs().max()) == 0.0
+
+
+def test_warp_host_tensors_are_staged_through_the_gpu(dev):
+    """tools/evaluate_dir_lab.py:217-222 hands Bilinear CPU tensors."""
+    from liftreg_b200 import net_utils
+    g = load_golden("warp_small")
+    out = net_utils.Bilinear(zero_boundary=True, using_scale=False, mode="nearest")(torch.from_numpy(g["img"]),
+                                                                                  torch.from_numpy(g["phi"]))
+    assert not out.is_cuda
+    assert np.array_equal(out.numpy(), g["out_zb1_us0_nearest"])
+
+
+def test_identity_map_bit_exact(dev):
+    from liftreg_b200 import net_utils
+    g = load_golden("identity_map")
+    assert np.array_equal(net_utils.identity_map((7, 9, 11)).cpu().numpy(), g["id_7_9_11"])
+    assert np.array_equal(net_utils.gen_identity_map([5, 6, 7], 1.0).cpu().numpy(), g["gen_5_6_7"])
+    assert np.array_equal(net_utils.identity_map((160, 160, 160))[:, ::16, ::16, ::16].cpu().numpy(), g["id_160"])
+
+
+def test_warp_cfg2_vs_reference_golden_and_fused_identity(dev):
+    """BASELINE configs[1] warp: 160^3, Bilinear(zero_boundary=True, using_scale=True) as the model builds it."""
+    from liftreg_b200 import net_utils, ops, synthetic
+    g = load_golden("warp_cfg2")
+    moving = cu(synthetic.hu_to_unit(synthetic.ct_phantom((160, 160, 160)))[None, None], dev)
+    disp = cu(synthetic.smooth_displacement((160, 160, 160))[None], dev)
+    phi = disp + net_utils.identity_map((160, 160, 160))[None]             # model :68
+    assert abs(float(phi.double().sum()) - float(g["phi_sum64"])) <= 1e-6 * abs(float(g["phi_sum64"])) + 1e-3
+    out = net_utils.Bilinear(zero_boundary=True, using_scale=True)(moving, phi)
+    o = out[0, 0].cpu().numpy()
+    assert rel_l2(o[::8, ::8, ::8], g["out_sub"]) <= TOL
+    assert rel_l2(o[80, 80, :], g["out_line"]) <= TOL
+    assert abs(np.sqrt((o.astype(np.float64) ** 2).sum()) - float(g["norm64"])) <= TOL * float(g["norm64"])
+    fused = ops.warp(moving, disp, zero_boundary=True, using_scale=True, disp_plus_identity=True)
+    assert torch.equal(fused, out)                                         # in-kernel identity == torch add
+
+
+@pytest.mark.parametrize("shape,B,C", [((1, 1, 1), 1, 1), ((3, 5, 2), 2, 3), ((17, 33, 129), 1, 2), ((2, 300, 70), 1, 1)])
+def test_warp_ragged_shapes_vs_oracle(dev, shape, B, C):
+    from liftreg_b200 import ops
+    from oracle import c_oracle
+    rs = np.random.RandomState(3)
+    img = rs.uniform(-1, 1, (B, C) + shape).astype(np.float32)
+    phi = rs.uniform(-1.3, 1.3, (B, 3) + shape).astype(np.float32)
+    for zb in (False, True):
+        for mode in ("bilinear", "nearest"):
+            out = ops.warp(cu(img, dev), cu(phi, dev), zero_boundary=zb, using_scale=True, mode=mode).cpu().numpy()
+            assert np.array_equal(out, c_oracle.warp_forward(img, phi, zb, True, mode)), (zb, mode)
+
+
+def test_warp_identity_is_idempotent_full_size(dev):
+    """Size-independent property at 160^3: warping by the identity map returns the image (to 1 ulp of the rescale)."""
+    from liftreg_b200 import net_utils, synthetic
+    moving = cu(synthetic.hu_to_unit(synthetic.ct_phantom((160, 160, 160)))[None, None], dev)
+    idm = net_utils.identity_map((160, 160, 160))[None]
+    out = net_utils.Bilinear(zero_boundary=True, using_scale=True)(moving, idm)
+    assert rel_l2(out.cpu().numpy(), moving.cpu().numpy()) <= TOL
+    out2 = net_utils.Bilinear(zero_boundary=False, using_scale=False)(moving, idm)
+    assert rel_l2(out2.cpu().numpy(), moving.cpu().numpy()) <= TOL
+
+
+def test_warp_backward_vs_oracle(dev):
+    from liftreg_b200 import ops
+    from oracle import c_oracle
+    rs = np.random.RandomState(12)
+    shape = (10, 13, 9)
+    img = rs.uniform(-1, 1, (2, 2) + shape).astype(np.float32)
+    phi = rs.uniform(-1.1, 1.1, (2, 3) + shape).astype(np.float32)
+    go = rs.randn(2, 2, *shape).astype(np.float32)
+    for zb in (False, True):
+        ti, tp = cu(img, dev).requires_grad_(True), cu(phi, dev).requires_grad_(True)
+        ops.warp(ti, tp, zero_boundary=zb, using_scale=True).backward(cu(go, dev))
+        gi, gp = c_oracle.warp_backward(go, img, phi, zb, True, "bilinear")
+        assert rel_l2(ti.grad.cpu().numpy(), gi) <= GRAD_TOL
+        assert rel_l2(tp.grad.cpu().numpy(), gp) <= GRAD_TOL
+
+
+# ------------------------------------------------------------------ host-buffer C-ABI entry points
+def test_host_entry_points_match_device_entry_points(dev):
+    import ctypes
+    from liftreg_b200 import _native, ops
+    lib = _native.lib()
+    g = load_golden("warp_small")
+    img, phi = np.ascontiguousarray(g["img"]), np.ascontiguousarray(g["phi"])
+    B, C, D, H, W = img.shape
+    out = np.empty_like(img)
+    ws = torch.empty(lib.lr_warp_forward_host_workspace_bytes(B, C, D, H, W), dtype=torch.uint8, device=dev)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _native.check(lib.lr_warp_forward_host(img.ctypes.data, phi.ctypes.data, B, C, D, H, W, 0, 0, 1, 0, out.ctypes.data,
+                                           ctypes.c_void_p(ws.data_ptr()), ws.numel(), st), "warp host")
+    assert np.array_equal(out, g["out_zb1_us1_bilinear"])
+    # too-small workspace is reported, not crashed on
+    rc = lib.lr_warp_forward_host(img.ctypes.data, phi.ctypes.data, B, C, D, H, W, 0, 0, 1, 0, out.ctypes.data,
+                                  ctypes.c_void_p(ws.data_ptr()), 16, st)
+    assert rc == -3 and b"workspace" in lib.lr_last_error()
+
+    gb = load_golden("backproj_small")
+    tp = np.ascontiguousarray(gb["target_proj"]); poses = np.ascontiguousarray(gb["poses"][0])
+    Bp, P, pw, ph = tp.shape
+    d, w, h = (int(s) for s in gb["img_shape"])
+    vol = np.empty((Bp, P, d, w, h), np.float32)
+    ws = torch.empty(lib.lr_backproject_forward_host_workspace_bytes(Bp, P, pw, ph, d, w, h), dtype=torch.uint8, device=dev)
+    _native.check(lib.lr_backproject_forward_host(tp.ctypes.data, ops._fp(poses), Bp, P, pw, ph, d, w, h, vol.ctypes.data,
+                                                  ctypes.c_void_p(ws.data_ptr()), ws.numel(), st), "backproject host")
+    assert np.array_equal(vol, gb["out"])
+
+
+# ------------------------------------------------------------------ error behaviour
+def test_bad_arguments_are_reported_not_crashed(dev):
+    import ctypes
+    from liftreg_b200 import _native, ops
+    lib = _native.lib()
+    t = torch.zeros(8, device=dev)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    p = ctypes.c_void_p(t.data_ptr())
+    assert lib.lr_warp_forward(p, p, 0, 1, 2, 2, 2, 0, 0, 1, 0, p, st) == -1
+    assert lib.lr_warp_forward(p, p, 1, 1, 2, 2, 2, 5, 0, 1, 0, p, st) == -1
+    assert lib.lr_warp_forward(None, p, 1, 1, 2, 2, 2, 0, 0, 1, 0, p, st) == -1
+    assert b"null" in lib.lr_last_error()
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ops.warp(torch.zeros(1, 1, 2, 2, 2), torch.zeros(1, 3, 2, 2, 2))
+    with pytest.raises(TypeError):
+        ops.warp(torch.zeros(1, 1, 2, 2, 2, device=dev, dtype=torch.float64), torch.zeros(1, 3, 2, 2, 2, device=dev))
+    with pytest.raises(ValueError):
+        ops.backproject(torch.zeros(1, 2, 4, 4, device=dev), np.zeros((3, 3), np.float32), (2, 2, 2))
+    with pytest.raises(NotImplementedError):
+        from liftreg_b200 import sdct_projection_utils as sdct
+        sdct.calculate_projection(np.zeros((2, 2, 2), np.float32), np.zeros((1, 3)), (2, 2), [2, 1, 1], (1, 1, 1), dev)
