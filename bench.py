@@ -1,0 +1,412 @@
+#!/usr/bin/env python
+"""Benchmark of the LiftReg resampling hot path on B200 (contract: see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg2|drr_cfg1|drr_cfg4]
+
+One "step" = one pass of the hot path over one batch of synthetic input.  Default workload = BASELINE.json
+configs[1]: backprojection of 4 limited-angle 256^2 DRRs into a 160^3 volume + displacement warp of the moving
+160^3 CT, batch 1 per GPU.  Units per step = 4*160^3 voxel-samples (backprojection) + 160^3 voxels (warp).
+
+  value   device-resident throughput: inputs already in HBM, CUDA-graph replay of the two kernels, CUDA events on
+          the launching stream, max over ranks.  Consecutive steps use different buffer sets (rotation of R sets,
+          R * 148 MB >> 126 MB L2) so every step reads cold inputs.
+  e2e     same metric through the host-buffer C-ABI calls (lr_backproject_forward_host + lr_warp_forward_host):
+          pinned host inputs -> H2D -> kernels -> D2H of both results, every step, synchronous.
+  roofline  dominant kernel, algorithmic bytes / mean launch duration (CUDA events, same rotation) vs measured HBM peak.
+  cpu_baseline  the reference's CPU path (oracle/torch_port.py, op-for-op torch restatement) on this box's host cores.
+
+N > 1 (torchrun): every rank owns one batch item (data-parallel sharding of the batch, no data-path collective),
+so per-GPU work is fixed ("weak"); value = all ranks' units / max-over-ranks time.
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "ray+voxel samples/s for DRR, backproj, warp; HBM GB/s vs peak at 1/2/4/8 B200"
+UNIT = "samples/s"
+VOL = (160, 160, 160)
+DET = (256, 256)
+P = 4
+ROTATION = 8
+
+
+def _peak_hbm():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _traffic(kernel):
+    """DRAM bytes per launch from the committed ncu --set full capture (profiles/), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(kernel)
+    except Exception:
+        return None
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML (what nvidia-smi reads) every 20 ms in a thread."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.util = [], set(), []
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            self.nv = None
+            self.err = repr(e)
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                util = nv.nvmlDeviceGetUtilizationRates(self.h).gpu
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                self.samples.append(mhz)
+                self.util.append(util)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def start(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples), "sm_mhz_min": int(min(self.samples)), "sm_mhz_max_seen": int(max(self.samples))}
+
+
+# ----------------------------------------------------------------------------------------------- inputs
+def make_inputs():
+    """Seeded synthetic cfg2 inputs on the host (numpy fp32)."""
+    from liftreg_b200 import synthetic
+    hu = synthetic.ct_phantom(VOL)
+    moving = synthetic.hu_to_unit(hu)[None, None]                          # (1,1,160,160,160) in [-1,1]
+    phi = (synthetic.smooth_displacement(VOL) + synthetic.identity_map_np(VOL))[None]   # (1,3,...) model :68
+    poses = synthetic.wrapper_poses(60.0, P, VOL[1])
+    return hu, moving, phi.astype(np.float32), poses
+
+
+# ----------------------------------------------------------------------------------------------- reference arm
+def cpu_reference_step_fn(moving, phi, target_proj, poses32, nz=None):
+    """The reference's CPU path for cfg2 (oracle/torch_port.py): backprojection grid cached like the model does
+    (:85-87), then Bilinear warp.  nz < 160 restricts both outputs to their first nz axial planes (a bounded sample:
+    grid_sample takes an output grid of any extent over the full input)."""
+    import torch
+    from oracle import torch_port
+    nz = VOL[0] if nz is None else int(nz)
+    grids = torch_port.backproj_grid(poses32[None], VOL, DET).permute(0, 1, 3, 4, 5, 2)
+    t_proj, t_moving, t_phi = torch.from_numpy(target_proj), torch.from_numpy(moving), torch.from_numpy(phi)
+    if nz < VOL[0]:
+        grids = grids[:, :, :nz].contiguous()
+        t_phi = t_phi[:, :, :nz].contiguous()
+
+    def step():
+        lifted = torch_port.backproject(t_proj, grids)
+        warped = torch_port.warp(t_moving, t_phi, zero_boundary=True, using_scale=True)
+        return lifted, warped
+
+    units = (P + 1) * nz * VOL[1] * VOL[2]
+    return step, units, nz
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (torch CPU ops, all host threads)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+    torch.set_num_threads(os.cpu_count())
+    from liftreg_b200 import synthetic
+    from oracle import torch_port
+    hu, moving, phi, poses = make_inputs()
+    poses32 = poses.astype(np.float32)
+    mu = synthetic.hu_to_mu(hu)
+    proj = torch_port.drr(mu, poses, DET, (2.2, 2.2, 2.2))                 # reference DRR on CPU makes the inputs
+    target_proj = synthetic.normalise_projection(proj)[None]
+    step, units, nz = cpu_reference_step_fn(moving, phi, target_proj, poses32)
+    step()
+    t0 = time.perf_counter(); step(); t_full = time.perf_counter() - t0
+    budget = 120.0
+    warm = max(1, min(args.warmup, 3))
+    sample = "full cfg2 step (B=1)"
+    if (args.steps + warm) * t_full > budget:                              # bounded sample: an axial slab of both outputs
+        nz = int(min(VOL[0], max(4, VOL[0] * budget / ((args.steps + warm) * t_full))))
+        step, units, nz = cpu_reference_step_fn(moving, phi, target_proj, poses32, nz)
+        sample = "first %d of %d axial planes of both outputs per step (bounded to ~%.0f s total)" % (nz, VOL[0], budget)
+    for _ in range(warm):
+        step()
+    times = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter(); step(); times.append(time.perf_counter() - t0)
+    ms = 1e3 * float(np.mean(times))
+    value = units / (ms * 1e-3)
+    sample += "; torch CPU backprojection (cached grid) + Bilinear warp via oracle/torch_port.py"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg2: backprojection 4x256^2 -> 160^3 + warp 160^3 (zeros, using_scale), batch 1 per GPU",
+                   "units_per_step": units, "full_step_s": t_full,
+                   "host": "CPU only (torch %s, %d threads, %d cpus)" % (torch.__version__, torch.get_num_threads(), os.cpu_count())},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from liftreg_b200 import _native, ops, synthetic
+    from liftreg_b200 import sdct_projection_utils as sdct
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    lib = _native.lib()
+
+    hu, moving, phi, poses = make_inputs()
+    poses32 = np.ascontiguousarray(poses.astype(np.float32))
+    mu = synthetic.hu_to_mu(hu)
+    proj = sdct.calculate_projection(mu, poses, DET, [1, 1, 1], (2.2, 2.2, 2.2), dev)     # our DRR makes the inputs
+    target_proj = synthetic.normalise_projection(proj)[None]                             # (1,4,256,256)
+
+    nv = VOL[0] * VOL[1] * VOL[2]
+    units_bp, units_warp = P * nv, nv
+    units = units_bp + units_warp
+    bytes_bp = 4 * units_bp + 4 * P * DET[0] * DET[1]          # 4 B write / voxel-sample + projections once
+    bytes_warp = 20 * units_warp                               # 4 out + 12 phi + 4 image per voxel
+
+    # R rotating buffer sets (distinct HBM) -> every step touches cold data: R*148 MB >> 126 MB L2
+    R = ROTATION
+    sets = []
+    for r in range(R):
+        sets.append(dict(proj=torch.from_numpy(target_proj).to(dev), moving=torch.from_numpy(moving).to(dev),
+                         phi=torch.from_numpy(phi).to(dev),
+                         lifted=torch.empty((1, P) + VOL, device=dev), warped=torch.empty((1, 1) + VOL, device=dev)))
+    pp = ops._fp(poses32)
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())
+
+    def k_backproject(s, st):
+        _native.check(lib.lr_backproject_forward(vp(s["proj"]), pp, 1, P, DET[0], DET[1], VOL[0], VOL[1], VOL[2],
+                                                 vp(s["lifted"]), P * nv, nv, st), "lr_backproject_forward")
+
+    def k_warp(s, st):
+        _native.check(lib.lr_warp_forward(vp(s["moving"]), vp(s["phi"]), 1, 1, VOL[0], VOL[1], VOL[2], 0, 0, 1, 0,
+                                          vp(s["warped"]), st), "lr_warp_forward")
+
+    def step(s, st):
+        k_backproject(s, st)
+        k_warp(s, st)
+
+    stream = torch.cuda.Stream(device=dev)
+
+    def capture(fn):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(stream):
+            st = ctypes.c_void_p(stream.cuda_stream)
+            fn(sets[0], st)                                     # module load / first-launch outside capture
+            stream.synchronize()
+            with torch.cuda.graph(g, stream=stream):
+                for r in range(R):
+                    fn(sets[r], st)
+        return g
+
+    def run_steps(graph, fn, n):
+        """exactly n steps on `stream`: graph replays of R steps + eager remainder."""
+        with torch.cuda.stream(stream):
+            for _ in range(n // R):
+                graph.replay()
+            st = ctypes.c_void_p(stream.cuda_stream)
+            for r in range(n % R):
+                fn(sets[r], st)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def timed(graph, fn, n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier(); torch.cuda.synchronize()
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+        run_steps(graph, fn, n)
+        with torch.cuda.stream(stream):
+            e1.record(stream)
+        torch.cuda.synchronize(); barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    _native.launch_count_reset()
+    g_step = capture(step)
+    launches_per_step = (_native.launch_count() - 2) // R       # counted at capture time (replays re-issue them)
+    g_bp, g_warp = capture(k_backproject), capture(k_warp)
+
+    sampler = ClockSampler(local)
+    run_steps(g_step, step, max(args.warmup, 3))                 # W untimed warm-up steps
+    torch.cuda.synchronize()
+    sampler.start()
+    total_ms = timed(g_step, step, args.steps)                   # EXACTLY K steps
+    ms_per_step = total_ms / args.steps
+    value = world * units / (ms_per_step * 1e-3)
+
+    # per-kernel mean launch duration, same rotation, same stream (enough launches to sample clocks under load)
+    n_k = max(args.steps, 4000)
+    run_steps(g_bp, k_backproject, 64); us_bp = 1e3 * timed(g_bp, k_backproject, n_k) / n_k
+    run_steps(g_warp, k_warp, 64); us_warp = 1e3 * timed(g_warp, k_warp, n_k) / n_k
+    n_long = int(min(200000, max(n_k, 1.0e6 / max(us_bp + us_warp, 1.0))))   # ~1 s of back-to-back steps for the clock record
+    sustained_ms = timed(g_step, step, n_long) / n_long
+
+    # ---- e2e through the host-buffer C-ABI (pinned host memory, H2D + kernels + D2H every step)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    h_proj, h_moving, h_phi = pin(target_proj), pin(moving), pin(phi)
+    h_lifted = torch.empty((1, P) + VOL).pin_memory()
+    h_warped = torch.empty((1, 1) + VOL).pin_memory()
+    ws_bp = torch.empty(lib.lr_backproject_forward_host_workspace_bytes(1, P, DET[0], DET[1], *VOL), dtype=torch.uint8, device=dev)
+    ws_w = torch.empty(lib.lr_warp_forward_host_workspace_bytes(1, 1, *VOL), dtype=torch.uint8, device=dev)
+    st = ctypes.c_void_p(stream.cuda_stream)
+
+    def e2e_step():
+        _native.check(lib.lr_backproject_forward_host(vp(h_proj), pp, 1, P, DET[0], DET[1], VOL[0], VOL[1], VOL[2],
+                                                      vp(h_lifted), vp(ws_bp), ws_bp.numel(), st), "backproject host")
+        _native.check(lib.lr_warp_forward_host(vp(h_moving), vp(h_phi), 1, 1, VOL[0], VOL[1], VOL[2], 0, 0, 1, 0,
+                                               vp(h_warped), vp(ws_w), ws_w.numel(), st), "warp host")
+
+    n_e2e = max(3, min(args.steps, 50))
+    for _ in range(3):
+        e2e_step()
+    barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        e2e_step()                                               # each call synchronises its stream before returning
+    torch.cuda.synchronize()
+    e2e_ms = 1e3 * (time.perf_counter() - t0) / n_e2e
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    clocks = sampler.stop()
+    h2d = 4 * (h_proj.numel() + h_moving.numel() + h_phi.numel())
+    d2h = 4 * (h_lifted.numel() + h_warped.numel())
+    # the e2e outputs are the same bits as the device-resident ones
+    assert torch.equal(h_warped, sets[0]["warped"].cpu()) and torch.equal(h_lifted, sets[0]["lifted"].cpu())
+
+    # ---- CPU baseline (rank 0, N=1 only): the reference's torch path on the host cores, bounded sample
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count())
+        cstep, cunits, _ = cpu_reference_step_fn(moving, phi, target_proj, poses32)
+        cstep()
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter(); lifted_ref, warped_ref = cstep(); ts.append(time.perf_counter() - t0)
+        cpu_baseline = {"value": cunits / min(ts), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                        "sample": "full cfg2 step (B=1) x3 after 1 warm-up, best; oracle/torch_port.py = the reference's "
+                                  "torch CPU ops (cached backprojection grid, Bilinear warp)",
+                        "ms_per_step": 1e3 * min(ts), "host_cpus": os.cpu_count()}
+        # parity of the benchmarked outputs against the CPU path, in the same run
+        def rl2(a, b):
+            a = a.double(); b = b.double()
+            return float(((a - b).norm() / b.norm()).item())
+        cpu_baseline["parity_rel_l2"] = {"backproject": rl2(sets[0]["lifted"].cpu(), lifted_ref),
+                                         "warp": rl2(sets[0]["warped"].cpu(), warped_ref)}
+
+    if rank == 0:
+        peak, peak_src = _peak_hbm()
+        kern = {
+            "backproject_forward_kernel": {"us": us_bp, "bytes": bytes_bp, "gbps": bytes_bp / us_bp * 1e-3,
+                                           "units_per_s": units_bp / us_bp * 1e6},
+            "warp_forward_kernel": {"us": us_warp, "bytes": bytes_warp, "gbps": bytes_warp / us_warp * 1e-3,
+                                    "units_per_s": units_warp / us_warp * 1e6},
+        }
+        for k in kern.values():
+            k["frac_of_hbm_peak"] = k["gbps"] / peak
+        dom = max(kern, key=lambda k: kern[k]["us"])
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cfg2: backprojection 4x256^2 -> 160^3 + warp 160^3 (zeros, using_scale), batch 1 per GPU",
+                       "units_per_step_per_gpu": units, "parallelism": "batch-sharded dp%d, no collective" % world,
+                       "l2": "rotating %d buffer sets (%.0f MB) > 126 MB L2; no flush kernel" % (R, R * 148.5),
+                       "launch": "CUDA graph of %d steps replayed; remainder launched eagerly" % R},
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbps"], "peak": peak, "unit": "GB/s",
+                         "frac": kern[dom]["gbps"] / peak, "traffic": _traffic(dom), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": kern[dom]["bytes"], "us_per_launch": kern[dom]["us"]},
+            "kernels": kern,
+            "sustained_ms_per_step": sustained_ms,
+            "cpu_baseline": cpu_baseline,
+            "e2e": {"value": world * units / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": n_e2e,
+                    "api": "lr_backproject_forward_host + lr_warp_forward_host (pinned host buffers, synchronous)"},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
