@@ -46,9 +46,10 @@ __device__ __forceinline__ AxisTap axis_tap(float centred, float s_c, float scal
     float a = add_rn(mul_rn(sub_rn(centred, s_c), scale), s_c);   // (x - s)*scale + s
     float g = mul_rn(div_rn(a, sizef), 2.0f);                     // / size * 2
     float ix = mul_rn(add_rn(g, 1.0f), half_sm1);                 // (g+1)*((S-1)/2)
-    float fl = floorf(ix);
+    ix = clamp_index(ix, half_sm1 * 2.0f + 3.0f);                 // beyond [-2, S+1] no tap is in bounds
+    float fl;
     AxisTap t;
-    t.i0 = __float2int_rd(ix);
+    floor_fi(ix, fl, t.i0);
     t.w1 = sub_rn(ix, fl);
     return t;
 }
@@ -58,10 +59,39 @@ __device__ __forceinline__ float view_scale(float sy, int w, int j) {
     return div_rn(sy, sub_rn(sy, y));
 }
 
+// Per-plane (u-axis) entry of the block's shared table: one LDS.128 per i instead of ~25 instructions.
+struct __align__(16) BpRow {
+    int off0;     // r0 * ph * 4: byte offset of detector row r0 inside the view
+    float n, s;   // iy - floor(iy), 1 - n
+    int mask;     // bit 0: row r0 inside the detector, bit 1: row r0+1 inside
+};
+
+// Builds the table; returns (block-uniformly) whether every plane of the chunk has both rows inside the detector.
+__device__ __forceinline__ bool build_row_table(BpRow *rows, const BpDims &g, int i_begin, int i_count, float sx,
+                                                float scale) {
+    int ok = 1;
+    if ((int)threadIdx.x < i_count) {
+        AxisTap t = axis_tap((float)(i_begin + (int)threadIdx.x) - g.half_d, sx, scale, g.pwf, g.hpw);
+        BpRow r;
+        r.off0 = t.i0 * g.ph * 4;
+        r.n = t.w1;
+        r.s = sub_rn(1.0f, t.w1);
+        r.mask = ((unsigned)t.i0 < (unsigned)g.pw ? 1 : 0) | ((unsigned)(t.i0 + 1) < (unsigned)g.pw ? 2 : 0);
+        rows[threadIdx.x] = r;
+        ok = r.mask == 3;
+    }
+    return __syncthreads_and(ok) != 0;
+}
+
+// ATen vector kernel: out = fma(se_v, n*w, fma(sw_v, n*e, fma(ne_v, s*w, nw_v * (s*e))))
+__device__ __forceinline__ float bilerp(float va, float vb, float vc, float vd, float s, float n, float e, float wq) {
+    const float nw = mul_rn(s, e), ne = mul_rn(s, wq), sw = mul_rn(n, e), se = mul_rn(n, wq);
+    return fma_rn(vd, se, fma_rn(vc, sw, fma_rn(vb, ne, mul_rn(va, nw))));
+}
+
 __global__ void __launch_bounds__(256)
     backproject_forward_kernel(const float *__restrict__ proj, float *__restrict__ out, BpDims g, BpPoses poses) {
-    __shared__ int s_row[BP_ICHUNK];     // row index iu0 of the detector for plane i
-    __shared__ float s_wn[BP_ICHUNK];    // n = iy - floor(iy)
+    __shared__ BpRow rows[BP_ICHUNK];
 
     const int j = blockIdx.x;
     const int i_begin = blockIdx.y * BP_ICHUNK;
@@ -70,38 +100,46 @@ __global__ void __launch_bounds__(256)
     const float sx = poses.s[pl][0], sy = poses.s[pl][1], sz = poses.s[pl][2];
     const float scale = view_scale(sy, g.w, j);
     const int i_count = min(BP_ICHUNK, g.d - i_begin);
+    const bool rows_ok = build_row_table(rows, g, i_begin, i_count, sx, scale);
 
-    if (threadIdx.x < i_count) {
-        AxisTap t = axis_tap((float)(i_begin + (int)threadIdx.x) - g.half_d, sx, scale, g.pwf, g.hpw);
-        s_row[threadIdx.x] = t.i0;
-        s_wn[threadIdx.x] = t.w1;
-    }
-    __syncthreads();
-
-    const float *pv = proj + (int64_t)p * g.proj_view_stride;
     const int64_t proj_batch = (int64_t)g.P * g.proj_view_stride;
+    const int64_t plane_bytes = (int64_t)g.w * g.h * 4;
+    const int row_bytes = g.ph * 4;
     for (int k = threadIdx.x; k < g.h; k += blockDim.x) {
-        AxisTap tv = axis_tap((float)k - g.half_h, sz, scale, g.phf, g.hph);
+        const AxisTap tv = axis_tap((float)k - g.half_h, sz, scale, g.phf, g.hph);
         const float wq = tv.w1, e = sub_rn(1.0f, wq);
         const bool c0 = (unsigned)tv.i0 < (unsigned)g.ph, c1 = (unsigned)(tv.i0 + 1) < (unsigned)g.ph;
-        float *o = out + (int64_t)p * g.out_chan_stride + ((int64_t)i_begin * g.w + j) * g.h + k;
-        for (int ii = 0; ii < i_count; ++ii) {
-            const int r0 = s_row[ii];
-            const float n = s_wn[ii], s = sub_rn(1.0f, n);
-            const bool rv0 = (unsigned)r0 < (unsigned)g.pw, rv1 = (unsigned)(r0 + 1) < (unsigned)g.pw;
-            const float nw = mul_rn(s, e), ne = mul_rn(s, wq), sw = mul_rn(n, e), se = mul_rn(n, wq);
-            const float *row0 = pv + (int64_t)r0 * g.ph + tv.i0;
-            const float *row1 = row0 + g.ph;
-            for (int b = 0; b < g.B; ++b) {
-                const float *q0 = row0 + b * proj_batch, *q1 = row1 + b * proj_batch;
-                const float va = (rv0 && c0) ? __ldg(q0) : 0.0f;
-                const float vb = (rv0 && c1) ? __ldg(q0 + 1) : 0.0f;
-                const float vc = (rv1 && c0) ? __ldg(q1) : 0.0f;
-                const float vd = (rv1 && c1) ? __ldg(q1 + 1) : 0.0f;
-                const float r = fma_rn(vd, se, fma_rn(vc, sw, fma_rn(vb, ne, mul_rn(va, nw))));
-                st_stream(o + b * g.out_batch_stride, r);
+        // geometry (table + v-part) is shared by all batch items; the batch loop is the outer one so that the
+        // per-sample inner loop stays branch-free: LDS.128, 4 weights, 4 loads, 1 mul + 3 fma, 1 store
+#pragma unroll 1
+        for (int b = 0; b < g.B; ++b) {
+            const char *pv = (const char *)(proj + b * proj_batch + (int64_t)p * g.proj_view_stride + tv.i0);
+            char *o = (char *)(out + b * g.out_batch_stride + (int64_t)p * g.out_chan_stride +
+                               ((int64_t)i_begin * g.w + j) * g.h + k);
+            if (rows_ok && c0 && c1) {
+                // every tap of every plane of this chunk is inside the detector (the common case)
+#pragma unroll 8
+                for (int ii = 0; ii < i_count; ++ii) {
+                    const BpRow r = rows[ii];
+                    const float *q0 = (const float *)(pv + r.off0);
+                    const float *q1 = (const float *)(pv + r.off0 + row_bytes);
+                    const float va = __ldg(q0), vb = __ldg(q0 + 1), vc = __ldg(q1), vd = __ldg(q1 + 1);
+                    st_stream((float *)o, bilerp(va, vb, vc, vd, r.s, r.n, e, wq));
+                    o += plane_bytes;
+                }
+            } else {
+                // rays leaving the detector: per-tap predicates (zeros padding)
+                for (int ii = 0; ii < i_count; ++ii) {
+                    const BpRow r = rows[ii];
+                    const float *q0 = (const float *)(pv + r.off0);
+                    const float *q1 = (const float *)(pv + r.off0 + row_bytes);
+                    const bool rv0 = r.mask & 1, rv1 = r.mask & 2;
+                    const float va = (rv0 && c0) ? __ldg(q0) : 0.0f, vb = (rv0 && c1) ? __ldg(q0 + 1) : 0.0f;
+                    const float vc = (rv1 && c0) ? __ldg(q1) : 0.0f, vd = (rv1 && c1) ? __ldg(q1 + 1) : 0.0f;
+                    st_stream((float *)o, bilerp(va, vb, vc, vd, r.s, r.n, e, wq));
+                    o += plane_bytes;
+                }
             }
-            o += (int64_t)g.w * g.h;
         }
     }
 }
@@ -109,8 +147,7 @@ __global__ void __launch_bounds__(256)
 // Adjoint wrt the projections: scatter grad_out * weight into the 4 detector taps (RED.ADD.F32).
 __global__ void __launch_bounds__(256)
     backproject_backward_kernel(const float *__restrict__ gout, float *__restrict__ gproj, BpDims g, BpPoses poses) {
-    __shared__ int s_row[BP_ICHUNK];
-    __shared__ float s_wn[BP_ICHUNK];
+    __shared__ BpRow rows[BP_ICHUNK];
     const int j = blockIdx.x;
     const int i_begin = blockIdx.y * BP_ICHUNK;
     const int pl = blockIdx.z;
@@ -118,35 +155,32 @@ __global__ void __launch_bounds__(256)
     const float sx = poses.s[pl][0], sy = poses.s[pl][1], sz = poses.s[pl][2];
     const float scale = view_scale(sy, g.w, j);
     const int i_count = min(BP_ICHUNK, g.d - i_begin);
-    if (threadIdx.x < i_count) {
-        AxisTap t = axis_tap((float)(i_begin + (int)threadIdx.x) - g.half_d, sx, scale, g.pwf, g.hpw);
-        s_row[threadIdx.x] = t.i0;
-        s_wn[threadIdx.x] = t.w1;
-    }
-    __syncthreads();
+    build_row_table(rows, g, i_begin, i_count, sx, scale);
     float *pv = gproj + (int64_t)p * g.proj_view_stride;
     const int64_t proj_batch = (int64_t)g.P * g.proj_view_stride;
+    const int plane = g.w * g.h;
     for (int k = threadIdx.x; k < g.h; k += blockDim.x) {
-        AxisTap tv = axis_tap((float)k - g.half_h, sz, scale, g.phf, g.hph);
+        const AxisTap tv = axis_tap((float)k - g.half_h, sz, scale, g.phf, g.hph);
         const float wq = tv.w1, e = sub_rn(1.0f, wq);
         const bool c0 = (unsigned)tv.i0 < (unsigned)g.ph, c1 = (unsigned)(tv.i0 + 1) < (unsigned)g.ph;
         const float *o = gout + (int64_t)p * g.out_chan_stride + ((int64_t)i_begin * g.w + j) * g.h + k;
         for (int ii = 0; ii < i_count; ++ii) {
-            const int r0 = s_row[ii];
-            const float n = s_wn[ii], s = sub_rn(1.0f, n);
-            const bool rv0 = (unsigned)r0 < (unsigned)g.pw, rv1 = (unsigned)(r0 + 1) < (unsigned)g.pw;
-            const float nw = mul_rn(s, e), ne = mul_rn(s, wq), sw = mul_rn(n, e), se = mul_rn(n, wq);
-            float *row0 = pv + (int64_t)r0 * g.ph + tv.i0;
-            float *row1 = row0 + g.ph;
+            const BpRow r = rows[ii];
+            const bool rv0 = r.mask & 1, rv1 = r.mask & 2;
+            const float nw = mul_rn(r.s, e), ne = mul_rn(r.s, wq), sw = mul_rn(r.n, e), se = mul_rn(r.n, wq);
+            float *q0 = pv + (r.off0 / 4 + tv.i0);
+            float *q1 = q0 + g.ph;
+            const float *ob = o;
+#pragma unroll 1
             for (int b = 0; b < g.B; ++b) {
-                const float go = ld_stream(o + b * g.out_batch_stride);
-                float *q0 = row0 + b * proj_batch, *q1 = row1 + b * proj_batch;
+                const float go = ld_stream(ob);
                 if (rv0 && c0) red_add(q0, mul_rn(nw, go));
                 if (rv0 && c1) red_add(q0 + 1, mul_rn(ne, go));
                 if (rv1 && c0) red_add(q1, mul_rn(sw, go));
                 if (rv1 && c1) red_add(q1 + 1, mul_rn(se, go));
+                q0 += proj_batch; q1 += proj_batch; ob += g.out_batch_stride;
             }
-            o += (int64_t)g.w * g.h;
+            o += plane;
         }
     }
 }
@@ -172,6 +206,7 @@ static int fill_dims(BpDims &g, int B, int P, int pw, int ph, int d, int w, int 
     LR_REQUIRE(B > 0 && P > 0 && pw > 0 && ph > 0 && d > 0 && w > 0 && h > 0,
                "backproject: non-positive dimension (B=%d P=%d pw=%d ph=%d d=%d w=%d h=%d)", B, P, pw, ph, d, w, h);
     LR_REQUIRE(d <= 65535 * BP_ICHUNK && w < (1 << 30), "backproject: volume too large for the launch grid");
+    LR_REQUIRE((int64_t)(pw + 4) * ph < (1ll << 31) && (int64_t)w * h < (1ll << 31), "backproject: detector / plane too large for 32-bit offsets");
     g.B = B; g.P = P; g.pw = pw; g.ph = ph; g.d = d; g.w = w; g.h = h; g.p0 = 0;
     g.half_d = (float)((double)d / 2.0); g.half_h = (float)((double)h / 2.0);
     g.pwf = (float)pw; g.phf = (float)ph;

@@ -34,6 +34,27 @@ __device__ __forceinline__ float div_const(float x, ConstDiv k) {
     return __fmaf_rn(r, k.rc, q0);
 }
 
+// floor(x) as float and int for |x| < 2^22, on the FP32/ALU pipes only.  FRND/F2I/I2F run on the XU pipe at 16
+// lanes/clk/SM and saturated it in the first version of these kernels (ncu: xu 95 %).  Adding 1.5*2^23 rounds x to
+// an integer that can be read straight out of the mantissa; one compare turns round-to-nearest into floor.
+// Callers clamp x to a few voxels around the volume first (samples further out have no in-bounds tap anyway).
+__device__ __forceinline__ void floor_fi(float x, float &f, int &i) {
+    const float M = 12582912.0f;                  // 1.5 * 2^23 = 0x4B400000
+    const float t = __fadd_rn(x, M);
+    const float r = __fsub_rn(t, M);              // exact: nearest integer to x
+    const int ri = __float_as_int(t) - 0x4B400000;
+    const bool up = r > x;                        // rounded up -> step back
+    f = up ? __fsub_rn(r, 1.0f) : r;
+    i = up ? ri - 1 : ri;
+}
+// nearbyint(x) (half to even) for |x| < 2^22, same trick without the compare
+__device__ __forceinline__ int rint_i(float x) {
+    return __float_as_int(__fadd_rn(x, 12582912.0f)) - 0x4B400000;
+}
+__device__ __forceinline__ float clamp_index(float x, float hi) {   // keep |x| < 2^22; NaN -> -2
+    return fminf(fmaxf(x, -2.0f), hi);
+}
+
 // Streaming (read-once / write-once) accesses: keep them out of L1 so the gather working set stays resident.
 __device__ __forceinline__ float ld_stream(const float *p) {
     float v;

@@ -12,9 +12,14 @@
 
 namespace lr {
 
+constexpr int WARP_TX = 32;   // threads along W (coalesced 128 B rows)
+constexpr int WARP_TY = 8;    // rows of H per block
+
 struct WarpDims {
     int C, D, H, W;
-    int64_t nvox;        // D*H*W
+    int nvox;            // D*H*W  (< 2^31: 32-bit voxel offsets; batch/channel offsets are 64-bit)
+    int HW;              // H*W
+    unsigned z_magic;    // ceil(2^32 / D): b = (blockIdx.z * z_magic) >> 32 for blockIdx.z < 65536
     float hx, hy, hz;    // (W-1)/2, (H-1)/2, (D-1)/2
     float mx, my, mz;    // W-1, H-1, D-1
     double sp0, sp1, sp2;  // 1/(D-1), 1/(H-1), 1/(W-1) as float64 (identity map, net_utils.py:81)
@@ -26,6 +31,7 @@ __device__ __forceinline__ float source_index(float g, float half_sm1, float sm1
     // ((g+1)/2)*(S-1) == RN(RN(g+1) * ((S-1)/2)): /2 is exact and (S-1)/2 is representable.
     float i = mul_rn(add_rn(g, 1.0f), half_sm1);
     if (PAD == LR_PAD_BORDER) i = fminf(sm1, fmaxf(i, 0.0f));
+    else i = clamp_index(i, sm1 + 2.0f);   // no tap is in bounds outside (-1, S): values there never matter
     return i;
 }
 
@@ -35,88 +41,119 @@ __device__ __forceinline__ float identity_coord(int idx, double spacing) {
     return sub_rn(mul_rn(v, 2.0f), 1.0f);
 }
 
-template <bool IDENT>
-__device__ __forceinline__ void load_phi(const float *__restrict__ phi_b, const WarpDims &g, int64_t vox, int z, int y,
-                                         int x, float &gx, float &gy, float &gz) {
-    // channel c of phi addresses volume axis c; grid_sample's x is the last axis (net_utils.py:27-30)
-    gz = ld_stream(phi_b + vox);
-    gy = ld_stream(phi_b + g.nvox + vox);
-    gx = ld_stream(phi_b + 2 * g.nvox + vox);
-    if (IDENT) {  // LiftRegDeformSubspaceBackproj.py:68  deform_field = disp_field + id_transform
-        gz = add_rn(gz, identity_coord(z, g.sp0));
-        gy = add_rn(gy, identity_coord(y, g.sp1));
-        gx = add_rn(gx, identity_coord(x, g.sp2));
-    }
+// Per-block identity-map table: the int->double conversions and fp64 multiplies are done by 41 threads once
+// instead of by every voxel (they run on the slow XU / fp64 pipes).
+struct IdentTable {
+    float x[WARP_TX], y[WARP_TY], z;
+};
+__device__ __forceinline__ void build_ident_table(IdentTable &t, const WarpDims &g, int x0, int y0, int z) {
+    const int tid = threadIdx.y * WARP_TX + threadIdx.x;
+    if (tid < WARP_TX) t.x[tid] = identity_coord(x0 + tid, g.sp2);
+    else if (tid < WARP_TX + WARP_TY) t.y[tid - WARP_TX] = identity_coord(y0 + tid - WARP_TX, g.sp1);
+    else if (tid == WARP_TX + WARP_TY) t.z = identity_coord(z, g.sp0);
+    __syncthreads();
 }
 
-template <int PAD, int MODE, bool SCALE, bool IDENT>
-__global__ void __launch_bounds__(256) warp_forward_kernel(const float *__restrict__ img, const float *__restrict__ phi,
-                                                           float *__restrict__ out, WarpDims g) {
-    const int plane = blockIdx.x * blockDim.x + threadIdx.x;  // index inside the (H,W) plane
-    if (plane >= g.H * g.W) return;
-    const int z = blockIdx.y, b = blockIdx.z;
-    const int y = plane / g.W, x = plane - y * g.W;
-    const int64_t vox = (int64_t)z * g.H * g.W + plane;
+template <int PAD, int MODE, bool SCALE, bool IDENT, bool C1>
+__global__ void __launch_bounds__(WARP_TX * WARP_TY)
+    warp_forward_kernel(const float *__restrict__ img, const float *__restrict__ phi, float *__restrict__ out, WarpDims g) {
+    __shared__ IdentTable ident;
+    const int x = blockIdx.x * WARP_TX + threadIdx.x;
+    const int y = blockIdx.y * WARP_TY + threadIdx.y;
+    const int b = (int)__umulhi(blockIdx.z, g.z_magic);
+    const int z = blockIdx.z - b * g.D;
+    if (IDENT) build_ident_table(ident, g, blockIdx.x * WARP_TX, blockIdx.y * WARP_TY, z);
+    if (x >= g.W || y >= g.H) return;
+    const int vox = z * g.HW + y * g.W + x;
 
-    float gx, gy, gz;
-    load_phi<IDENT>(phi + (int64_t)b * 3 * g.nvox, g, vox, z, y, x, gx, gy, gz);
+    // channel c of phi addresses volume axis c; grid_sample's x is the last axis (net_utils.py:27-30)
+    const float *phi_b = phi + (int64_t)b * 3 * g.nvox + vox;
+    float gz = ld_stream(phi_b), gy = ld_stream(phi_b + g.nvox), gx = ld_stream(phi_b + 2 * (int64_t)g.nvox);
+    if (IDENT) {  // LiftRegDeformSubspaceBackproj.py:68  deform_field = disp_field + id_transform
+        gz = add_rn(gz, ident.z);
+        gy = add_rn(gy, ident.y[threadIdx.y]);
+        gx = add_rn(gx, ident.x[threadIdx.x]);
+    }
     const float ix = source_index<PAD>(gx, g.hx, g.mx);
     const float iy = source_index<PAD>(gy, g.hy, g.my);
     const float iz = source_index<PAD>(gz, g.hz, g.mz);
 
-    const float *src = img + (int64_t)b * g.C * g.nvox;
-    float *dst = out + (int64_t)b * g.C * g.nvox + vox;
+    const int nchan = C1 ? 1 : g.C;   // C == 1 (the moving CT, label maps) gets a loop-free instantiation
+    const float *src = img + (int64_t)b * nchan * g.nvox;
+    float *dst = out + (int64_t)b * nchan * g.nvox + vox;
 
     if (MODE == LR_MODE_NEAREST) {
-        const int xn = __float2int_rn(ix), yn = __float2int_rn(iy), zn = __float2int_rn(iz);  // nearbyint: half to even
+        const int xn = rint_i(ix), yn = rint_i(iy), zn = rint_i(iz);  // nearbyint: half to even
         const bool ok = (unsigned)xn < (unsigned)g.W && (unsigned)yn < (unsigned)g.H && (unsigned)zn < (unsigned)g.D;
-        const int64_t off = ((int64_t)zn * g.H + yn) * g.W + xn;
-        for (int c = 0; c < g.C; ++c) {
+        const int off = zn * g.HW + yn * g.W + xn;
+        for (int c = 0; c < nchan; ++c) {
             float v = 0.0f;
             if (ok) {
-                v = __ldg(src + c * g.nvox + off);
+                v = __ldg(src + (int64_t)c * g.nvox + off);
                 if (SCALE) v = mul_rn(add_rn(v, 1.0f), 0.5f);
             }
             if (SCALE) v = sub_rn(mul_rn(v, 2.0f), 1.0f);
-            st_stream(dst + c * g.nvox, v);
+            st_stream(dst + (int64_t)c * g.nvox, v);
         }
         return;
     }
 
-    const float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
-    const int x0 = __float2int_rd(ix), y0 = __float2int_rd(iy), z0 = __float2int_rd(iz);
+    float fx, fy, fz;
+    int x0, y0, z0;
+    floor_fi(ix, fx, x0);
+    floor_fi(iy, fy, y0);
+    floor_fi(iz, fz, z0);
     const float wx1 = sub_rn(ix, fx), wx0 = sub_rn(add_rn(fx, 1.0f), ix);
     const float wy1 = sub_rn(iy, fy), wy0 = sub_rn(add_rn(fy, 1.0f), iy);
     const float wz1 = sub_rn(iz, fz), wz0 = sub_rn(add_rn(fz, 1.0f), iz);
     const float a00 = mul_rn(wx0, wy0), a10 = mul_rn(wx1, wy0), a01 = mul_rn(wx0, wy1), a11 = mul_rn(wx1, wy1);
     const float wt[8] = {mul_rn(a00, wz0), mul_rn(a10, wz0), mul_rn(a01, wz0), mul_rn(a11, wz0),
                          mul_rn(a00, wz1), mul_rn(a10, wz1), mul_rn(a01, wz1), mul_rn(a11, wz1)};
+    const int base = z0 * g.HW + y0 * g.W + x0;
+    // all eight taps inside the volume <=> 0 <= x0 <= W-2 etc.: the common case, no per-tap predicates
+    const bool interior = (unsigned)x0 < (unsigned)(g.W - 1) && (unsigned)y0 < (unsigned)(g.H - 1) &&
+                          (unsigned)z0 < (unsigned)(g.D - 1);
+    if (interior) {
+#pragma unroll 1
+        for (int c = 0; c < nchan; ++c) {
+            const float *s = src + (int64_t)c * g.nvox + base;
+            float v[8];
+            v[0] = __ldg(s); v[1] = __ldg(s + 1); v[2] = __ldg(s + g.W); v[3] = __ldg(s + g.W + 1);
+            const float *s1 = s + g.HW;
+            v[4] = __ldg(s1); v[5] = __ldg(s1 + 1); v[6] = __ldg(s1 + g.W); v[7] = __ldg(s1 + g.W + 1);
+            float acc = 0.0f;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {   // ATen: out += val * w, separately rounded, in tap order
+                float val = v[t];
+                if (SCALE) val = mul_rn(add_rn(val, 1.0f), 0.5f);   // net_utils.py:50 (img+1)/2, fused per tap
+                acc = add_rn(acc, mul_rn(val, wt[t]));
+            }
+            if (SCALE) acc = sub_rn(mul_rn(acc, 2.0f), 1.0f);       // net_utils.py:52
+            st_stream(dst + (int64_t)c * g.nvox, acc);
+        }
+        return;
+    }
+    // boundary voxels: per-tap bounds test, out-of-bounds taps are skipped (zeros padding)
     const bool vx0 = (unsigned)x0 < (unsigned)g.W, vx1 = (unsigned)(x0 + 1) < (unsigned)g.W;
     const bool vy0 = (unsigned)y0 < (unsigned)g.H, vy1 = (unsigned)(y0 + 1) < (unsigned)g.H;
     const bool vz0 = (unsigned)z0 < (unsigned)g.D, vz1 = (unsigned)(z0 + 1) < (unsigned)g.D;
     const bool ok[8] = {vx0 && vy0 && vz0, vx1 && vy0 && vz0, vx0 && vy1 && vz0, vx1 && vy1 && vz0,
                         vx0 && vy0 && vz1, vx1 && vy0 && vz1, vx0 && vy1 && vz1, vx1 && vy1 && vz1};
-    const int64_t base = ((int64_t)z0 * g.H + y0) * g.W + x0;
-    const int64_t sy = g.W, sz = (int64_t)g.H * g.W;
-    const int64_t off[8] = {base, base + 1, base + sy, base + sy + 1, base + sz, base + sz + 1, base + sz + sy,
-                            base + sz + sy + 1};
-
-    for (int c = 0; c < g.C; ++c) {
-        const float *s = src + c * g.nvox;
-        float v[8];
-#pragma unroll
-        for (int t = 0; t < 8; ++t) v[t] = ok[t] ? __ldg(s + off[t]) : 0.0f;
+    const int off[8] = {0, 1, g.W, g.W + 1, g.HW, g.HW + 1, g.HW + g.W, g.HW + g.W + 1};
+#pragma unroll 1
+    for (int c = 0; c < nchan; ++c) {
+        const float *s = src + (int64_t)c * g.nvox + base;
         float acc = 0.0f;
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
-            if (ok[t]) {  // ATen skips out-of-bounds taps; in-bounds taps are  out += val * w  (no fma)
-                float val = v[t];
-                if (SCALE) val = mul_rn(add_rn(val, 1.0f), 0.5f);  // net_utils.py:50 (img+1)/2, fused per tap
+            if (ok[t]) {
+                float val = __ldg(s + off[t]);
+                if (SCALE) val = mul_rn(add_rn(val, 1.0f), 0.5f);
                 acc = add_rn(acc, mul_rn(val, wt[t]));
             }
         }
-        if (SCALE) acc = sub_rn(mul_rn(acc, 2.0f), 1.0f);  // net_utils.py:52
-        st_stream(dst + c * g.nvox, acc);
+        if (SCALE) acc = sub_rn(mul_rn(acc, 2.0f), 1.0f);
+        st_stream(dst + (int64_t)c * g.nvox, acc);
     }
 }
 
@@ -124,30 +161,43 @@ __global__ void __launch_bounds__(256) warp_forward_kernel(const float *__restri
 // Follows ATen grid_sampler_3d_backward: gix -= tnw_val*(y1-y)*(z1-z)*gOut ... ; grad_grid = (S-1)/2 * gi,
 // zeroed where a border-clipped coordinate is outside (clip_coordinates_set_grad).
 template <int PAD, bool SCALE, bool IDENT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(WARP_TX * WARP_TY)
     warp_backward_kernel(const float *__restrict__ gout, const float *__restrict__ img, const float *__restrict__ phi,
                          float *__restrict__ gimg, float *__restrict__ gphi, WarpDims g) {
-    const int plane = blockIdx.x * blockDim.x + threadIdx.x;
-    if (plane >= g.H * g.W) return;
-    const int z = blockIdx.y, b = blockIdx.z;
-    const int y = plane / g.W, x = plane - y * g.W;
-    const int64_t vox = (int64_t)z * g.H * g.W + plane;
+    __shared__ IdentTable ident;
+    const int x = blockIdx.x * WARP_TX + threadIdx.x;
+    const int y = blockIdx.y * WARP_TY + threadIdx.y;
+    const int b = (int)__umulhi(blockIdx.z, g.z_magic);
+    const int z = blockIdx.z - b * g.D;
+    if (IDENT) build_ident_table(ident, g, blockIdx.x * WARP_TX, blockIdx.y * WARP_TY, z);
+    if (x >= g.W || y >= g.H) return;
+    const int vox = z * g.HW + y * g.W + x;
 
-    float gx, gy, gz;
-    load_phi<IDENT>(phi + (int64_t)b * 3 * g.nvox, g, vox, z, y, x, gx, gy, gz);
+    const float *phi_b = phi + (int64_t)b * 3 * g.nvox + vox;
+    float gz = ld_stream(phi_b), gy = ld_stream(phi_b + g.nvox), gx = ld_stream(phi_b + 2 * (int64_t)g.nvox);
+    if (IDENT) {
+        gz = add_rn(gz, ident.z);
+        gy = add_rn(gy, ident.y[threadIdx.y]);
+        gx = add_rn(gx, ident.x[threadIdx.x]);
+    }
     float ix = mul_rn(add_rn(gx, 1.0f), g.hx), iy = mul_rn(add_rn(gy, 1.0f), g.hy), iz = mul_rn(add_rn(gz, 1.0f), g.hz);
     float mx = g.hx, my = g.hy, mz = g.hz;
     if (PAD == LR_PAD_BORDER) {
         if (ix <= 0.0f) { ix = 0.0f; mx = 0.0f; } else if (ix >= g.mx) { ix = g.mx; mx = 0.0f; }
         if (iy <= 0.0f) { iy = 0.0f; my = 0.0f; } else if (iy >= g.my) { iy = g.my; my = 0.0f; }
         if (iz <= 0.0f) { iz = 0.0f; mz = 0.0f; } else if (iz >= g.mz) { iz = g.mz; mz = 0.0f; }
+    } else {
+        ix = clamp_index(ix, g.mx + 2.0f); iy = clamp_index(iy, g.my + 2.0f); iz = clamp_index(iz, g.mz + 2.0f);
     }
-    const float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
-    const int x0 = __float2int_rd(ix), y0 = __float2int_rd(iy), z0 = __float2int_rd(iz);
+    float fx, fy, fz;
+    int x0, y0, z0;
+    floor_fi(ix, fx, x0);
+    floor_fi(iy, fy, y0);
+    floor_fi(iz, fz, z0);
     const float wx[2] = {sub_rn(add_rn(fx, 1.0f), ix), sub_rn(ix, fx)};
     const float wy[2] = {sub_rn(add_rn(fy, 1.0f), iy), sub_rn(iy, fy)};
     const float wz[2] = {sub_rn(add_rn(fz, 1.0f), iz), sub_rn(iz, fz)};
-    const int64_t base = ((int64_t)z0 * g.H + y0) * g.W + x0;
+    const int base = z0 * g.HW + y0 * g.W + x0;
 
     float gix = 0.0f, giy = 0.0f, giz = 0.0f;
     for (int c = 0; c < g.C; ++c) {
@@ -160,7 +210,7 @@ __global__ void __launch_bounds__(256)
             const bool ok = (unsigned)(x0 + tx) < (unsigned)g.W && (unsigned)(y0 + ty) < (unsigned)g.H &&
                             (unsigned)(z0 + tz) < (unsigned)g.D;
             if (!ok) continue;
-            const int64_t o = chan + base + tx + (int64_t)ty * g.W + (int64_t)tz * g.H * g.W;
+            const int64_t o = chan + base + tx + ty * g.W + tz * g.HW;
             if (gimg) {
                 float wv = mul_rn(mul_rn(mul_rn(wx[tx], wy[ty]), wz[tz]), go);
                 red_add(gimg + o, SCALE ? mul_rn(wv, 0.5f) : wv);
@@ -181,19 +231,21 @@ __global__ void __launch_bounds__(256)
         float *gp = gphi + (int64_t)b * 3 * g.nvox + vox;
         st_stream(gp, mul_rn(mz, giz));
         st_stream(gp + g.nvox, mul_rn(my, giy));
-        st_stream(gp + 2 * g.nvox, mul_rn(mx, gix));
+        st_stream(gp + 2 * (int64_t)g.nvox, mul_rn(mx, gix));
     }
 }
 
-__global__ void identity_map_kernel(float *__restrict__ out, WarpDims g) {
-    const int plane = blockIdx.x * blockDim.x + threadIdx.x;
-    if (plane >= g.H * g.W) return;
-    const int z = blockIdx.y;
-    const int y = plane / g.W, x = plane - y * g.W;
-    const int64_t vox = (int64_t)z * g.H * g.W + plane;
-    out[vox] = identity_coord(z, g.sp0);
-    out[g.nvox + vox] = identity_coord(y, g.sp1);
-    out[2 * g.nvox + vox] = identity_coord(x, g.sp2);
+__global__ void __launch_bounds__(WARP_TX * WARP_TY) identity_map_kernel(float *__restrict__ out, WarpDims g) {
+    __shared__ IdentTable ident;
+    const int x = blockIdx.x * WARP_TX + threadIdx.x;
+    const int y = blockIdx.y * WARP_TY + threadIdx.y;
+    const int z = blockIdx.z;
+    build_ident_table(ident, g, blockIdx.x * WARP_TX, blockIdx.y * WARP_TY, z);
+    if (x >= g.W || y >= g.H) return;
+    const int vox = z * g.HW + y * g.W + x;
+    out[vox] = ident.z;
+    out[(int64_t)g.nvox + vox] = ident.y[threadIdx.y];
+    out[2 * (int64_t)g.nvox + vox] = ident.x[threadIdx.x];
 }
 
 __global__ void atten_coef_kernel(const float *__restrict__ hu, float *__restrict__ mu, int64_t n) {
@@ -206,7 +258,9 @@ __global__ void atten_coef_kernel(const float *__restrict__ hu, float *__restric
 static WarpDims make_dims(int C, int D, int H, int W) {
     WarpDims g;
     g.C = C; g.D = D; g.H = H; g.W = W;
-    g.nvox = (int64_t)D * H * W;
+    g.nvox = D * H * W;
+    g.HW = H * W;
+    g.z_magic = (unsigned)(((1ull << 32) + (unsigned)D - 1) / (unsigned)D);
     g.hx = (float)(W - 1) / 2.0f; g.hy = (float)(H - 1) / 2.0f; g.hz = (float)(D - 1) / 2.0f;
     g.mx = (float)(W - 1); g.my = (float)(H - 1); g.mz = (float)(D - 1);
     g.sp0 = 1.0 / (double)(D - 1); g.sp1 = 1.0 / (double)(H - 1); g.sp2 = 1.0 / (double)(W - 1);
@@ -215,34 +269,48 @@ static WarpDims make_dims(int C, int D, int H, int W) {
 
 static int check_warp_args(int B, int C, int D, int H, int W, int padding, int mode) {
     LR_REQUIRE(B > 0 && C > 0 && D > 0 && H > 0 && W > 0, "warp: non-positive dimension (B=%d C=%d D=%d H=%d W=%d)", B, C, D, H, W);
-    LR_REQUIRE(B <= 65535 && D <= 65535, "warp: B and D must be <= 65535 (grid limits)");
-    LR_REQUIRE((int64_t)H * W < (1ll << 31), "warp: H*W too large");
+    LR_REQUIRE((int64_t)D * H * W < (1ll << 31) - 2 * (int64_t)H * W - 4, "warp: D*H*W must fit 32-bit voxel offsets");
+    LR_REQUIRE(D < 65536 && (H + WARP_TY - 1) / WARP_TY <= 65535, "warp: D and H/8 must be < 65536 (grid limits)");
     LR_REQUIRE(padding == LR_PAD_ZEROS || padding == LR_PAD_BORDER, "warp: padding must be 0 (zeros) or 1 (border)");
     LR_REQUIRE(mode == LR_MODE_LINEAR || mode == LR_MODE_NEAREST, "warp: mode must be 0 (linear) or 1 (nearest)");
     return LR_OK;
 }
 
+// grid.z = D * (batch items of this launch) must stay <= 65535: batches are launched in chunks
+static int batch_chunk(int D) { return 65535 / D > 0 ? 65535 / D : 1; }
+static dim3 warp_grid(int nb, int D, int H, int W) {
+    return dim3((unsigned)((W + WARP_TX - 1) / WARP_TX), (unsigned)((H + WARP_TY - 1) / WARP_TY), (unsigned)(D * nb));
+}
+
 template <int PAD, int MODE>
 static void launch_fwd(bool scale, bool ident, dim3 grid, cudaStream_t st, const float *img, const float *phi, float *out,
                        const WarpDims &g) {
+    const dim3 blk(WARP_TX, WARP_TY);
+#define LR_LAUNCH_FWD(S, I)                                                                                  \
+    do {                                                                                                     \
+        if (g.C == 1) warp_forward_kernel<PAD, MODE, S, I, true><<<grid, blk, 0, st>>>(img, phi, out, g);     \
+        else warp_forward_kernel<PAD, MODE, S, I, false><<<grid, blk, 0, st>>>(img, phi, out, g);             \
+    } while (0)
     if (scale) {
-        if (ident) warp_forward_kernel<PAD, MODE, true, true><<<grid, 256, 0, st>>>(img, phi, out, g);
-        else warp_forward_kernel<PAD, MODE, true, false><<<grid, 256, 0, st>>>(img, phi, out, g);
+        if (ident) LR_LAUNCH_FWD(true, true);
+        else LR_LAUNCH_FWD(true, false);
     } else {
-        if (ident) warp_forward_kernel<PAD, MODE, false, true><<<grid, 256, 0, st>>>(img, phi, out, g);
-        else warp_forward_kernel<PAD, MODE, false, false><<<grid, 256, 0, st>>>(img, phi, out, g);
+        if (ident) LR_LAUNCH_FWD(false, true);
+        else LR_LAUNCH_FWD(false, false);
     }
+#undef LR_LAUNCH_FWD
 }
 
 template <int PAD>
 static void launch_bwd(bool scale, bool ident, dim3 grid, cudaStream_t st, const float *gout, const float *img,
                        const float *phi, float *gimg, float *gphi, const WarpDims &g) {
+    const dim3 blk(WARP_TX, WARP_TY);
     if (scale) {
-        if (ident) warp_backward_kernel<PAD, true, true><<<grid, 256, 0, st>>>(gout, img, phi, gimg, gphi, g);
-        else warp_backward_kernel<PAD, true, false><<<grid, 256, 0, st>>>(gout, img, phi, gimg, gphi, g);
+        if (ident) warp_backward_kernel<PAD, true, true><<<grid, blk, 0, st>>>(gout, img, phi, gimg, gphi, g);
+        else warp_backward_kernel<PAD, true, false><<<grid, blk, 0, st>>>(gout, img, phi, gimg, gphi, g);
     } else {
-        if (ident) warp_backward_kernel<PAD, false, true><<<grid, 256, 0, st>>>(gout, img, phi, gimg, gphi, g);
-        else warp_backward_kernel<PAD, false, false><<<grid, 256, 0, st>>>(gout, img, phi, gimg, gphi, g);
+        if (ident) warp_backward_kernel<PAD, false, true><<<grid, blk, 0, st>>>(gout, img, phi, gimg, gphi, g);
+        else warp_backward_kernel<PAD, false, false><<<grid, blk, 0, st>>>(gout, img, phi, gimg, gphi, g);
     }
 }
 
@@ -255,17 +323,24 @@ extern "C" int lr_warp_forward(const float *img, const float *phi, int B, int C,
     LR_REQUIRE(img && phi && out, "warp_forward: null pointer");
     if (int e = check_warp_args(B, C, D, H, W, padding, mode)) return e;
     WarpDims g = make_dims(C, D, H, W);
-    dim3 grid((unsigned)((H * W + 255) / 256), (unsigned)D, (unsigned)B);
     cudaStream_t st = as_stream(stream);
     const bool sc = using_scale != 0, id = disp_plus_identity != 0;
-    if (padding == LR_PAD_ZEROS) {
-        if (mode == LR_MODE_LINEAR) launch_fwd<LR_PAD_ZEROS, LR_MODE_LINEAR>(sc, id, grid, st, img, phi, out, g);
-        else launch_fwd<LR_PAD_ZEROS, LR_MODE_NEAREST>(sc, id, grid, st, img, phi, out, g);
-    } else {
-        if (mode == LR_MODE_LINEAR) launch_fwd<LR_PAD_BORDER, LR_MODE_LINEAR>(sc, id, grid, st, img, phi, out, g);
-        else launch_fwd<LR_PAD_BORDER, LR_MODE_NEAREST>(sc, id, grid, st, img, phi, out, g);
+    const int chunk = batch_chunk(D);
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+        const int nb = B - b0 < chunk ? B - b0 : chunk;
+        const dim3 grid = warp_grid(nb, D, H, W);
+        const float *im = img + (int64_t)b0 * C * g.nvox, *ph = phi + (int64_t)b0 * 3 * g.nvox;
+        float *o = out + (int64_t)b0 * C * g.nvox;
+        if (padding == LR_PAD_ZEROS) {
+            if (mode == LR_MODE_LINEAR) launch_fwd<LR_PAD_ZEROS, LR_MODE_LINEAR>(sc, id, grid, st, im, ph, o, g);
+            else launch_fwd<LR_PAD_ZEROS, LR_MODE_NEAREST>(sc, id, grid, st, im, ph, o, g);
+        } else {
+            if (mode == LR_MODE_LINEAR) launch_fwd<LR_PAD_BORDER, LR_MODE_LINEAR>(sc, id, grid, st, im, ph, o, g);
+            else launch_fwd<LR_PAD_BORDER, LR_MODE_NEAREST>(sc, id, grid, st, im, ph, o, g);
+        }
+        if (int e = check_launch("warp_forward_kernel")) return e;
     }
-    return check_launch("warp_forward_kernel");
+    return LR_OK;
 }
 
 extern "C" int lr_warp_backward(const float *grad_out, const float *img, const float *phi, int B, int C, int D, int H,
@@ -285,19 +360,26 @@ extern "C" int lr_warp_backward(const float *grad_out, const float *img, const f
         if (ce != cudaSuccess) { set_error("warp_backward: memset failed: %s", cudaGetErrorString(ce)); return LR_ERR_CUDA; }
         return LR_OK;
     }
-    dim3 grid((unsigned)((H * W + 255) / 256), (unsigned)D, (unsigned)B);
     const bool sc = using_scale != 0, id = disp_plus_identity != 0;
-    if (padding == LR_PAD_ZEROS) launch_bwd<LR_PAD_ZEROS>(sc, id, grid, st, grad_out, img, phi, grad_img, grad_phi, g);
-    else launch_bwd<LR_PAD_BORDER>(sc, id, grid, st, grad_out, img, phi, grad_img, grad_phi, g);
-    return check_launch("warp_backward_kernel");
+    const int chunk = batch_chunk(D);
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+        const int nb = B - b0 < chunk ? B - b0 : chunk;
+        const dim3 grid = warp_grid(nb, D, H, W);
+        const int64_t io = (int64_t)b0 * C * g.nvox, po = (int64_t)b0 * 3 * g.nvox;
+        float *gi = grad_img ? grad_img + io : nullptr, *gp = grad_phi ? grad_phi + po : nullptr;
+        if (padding == LR_PAD_ZEROS) launch_bwd<LR_PAD_ZEROS>(sc, id, grid, st, grad_out + io, img + io, phi + po, gi, gp, g);
+        else launch_bwd<LR_PAD_BORDER>(sc, id, grid, st, grad_out + io, img + io, phi + po, gi, gp, g);
+        if (int e = check_launch("warp_backward_kernel")) return e;
+    }
+    return LR_OK;
 }
 
 extern "C" int lr_identity_map(int D, int H, int W, float *out, lr_stream_t stream) {
     LR_REQUIRE(out, "identity_map: null pointer");
     LR_REQUIRE(D > 1 && H > 1 && W > 1 && D <= 65535, "identity_map: each size must be in [2, 65535]");
+    LR_REQUIRE((int64_t)D * H * W < (1ll << 31), "identity_map: D*H*W must fit 32 bits");
     WarpDims g = make_dims(1, D, H, W);
-    dim3 grid((unsigned)((H * W + 255) / 256), (unsigned)D, 1);
-    identity_map_kernel<<<grid, 256, 0, as_stream(stream)>>>(out, g);
+    identity_map_kernel<<<warp_grid(1, D, H, W), dim3(WARP_TX, WARP_TY), 0, as_stream(stream)>>>(out, g);
     return check_launch("identity_map_kernel");
 }
 
