@@ -304,6 +304,45 @@ def run_b200(args):
     n_long = int(min(200000, max(n_k, 1.0e6 / max(us_bp + us_warp, 1.0))))   # ~1 s of back-to-back steps for the clock record
     sustained_ms = timed(g_step, step, n_long) / n_long
 
+    # ---- DRR forward (BASELINE configs[0] geometry: 160^3, 4 views / 60 deg, 240^2 and 256^2 detectors), reported
+    # next to the headline because the north star names all three operators.  Nominal ray-samples = P*rd*rh*w.
+    drr_extra = {}
+    if rank == 0:
+        mus = [torch.from_numpy(mu)[None].to(dev) for _ in range(R)]
+        sp3 = np.array([2.2, 2.2, 2.2], np.float32)
+        poses64 = np.ascontiguousarray(poses, np.float64)
+        for det in ((240, 240), (256, 256)):
+            outs = [torch.empty((1, P) + det, device=dev) for _ in range(R)]
+
+            def k_drr(sidx, stx, det=det, outs=outs):
+                _native.check(lib.lr_drr_forward(vp(mus[sidx]), 1, VOL[0], VOL[1], VOL[2], ops._dp(poses64), 1, P, det[0], det[1],
+                                                 ops._fp(sp3), 0, ctypes.c_float(0.1), vp(outs[sidx]), stx), "lr_drr_forward")
+
+            g_drr = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(stream):
+                stx = ctypes.c_void_p(stream.cuda_stream)
+                k_drr(0, stx); stream.synchronize()
+                with torch.cuda.graph(g_drr, stream=stream):
+                    for r in range(R):
+                        k_drr(r, stx)
+            n_d = 40 * R
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
+                for _ in range(4):
+                    g_drr.replay()
+                e0.record(stream)
+                for _ in range(n_d // R):
+                    g_drr.replay()
+                e1.record(stream)
+            torch.cuda.synchronize()
+            us = 1e3 * e0.elapsed_time(e1) / n_d
+            nominal = P * det[0] * det[1] * VOL[1]
+            comp_bytes = 4 * nv + 4 * P * det[0] * det[1]
+            drr_extra["%dx%d" % det] = {
+                "us": us, "nominal_ray_samples": nominal, "samples_per_s": nominal / us * 1e6,
+                "compulsory_bytes": comp_bytes, "gbps_compulsory": comp_bytes / us * 1e-3,
+                "gather_model_gbps": 16.0 * nominal / us * 1e-3}
+
     # ---- e2e through the host-buffer C-ABI (pinned host memory, H2D + kernels + D2H every step)
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     h_proj, h_moving, h_phi = pin(target_proj), pin(moving), pin(phi)
@@ -381,6 +420,7 @@ def run_b200(args):
                          "frac": kern[dom]["gbps"] / peak, "traffic": _traffic(dom), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": kern[dom]["bytes"], "us_per_launch": kern[dom]["us"]},
             "kernels": kern,
+            "drr_forward_cfg1": {k: dict(v, frac_of_hbm_peak_compulsory=v["gbps_compulsory"] / peak) for k, v in drr_extra.items()},
             "sustained_ms_per_step": sustained_ms,
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": world * units / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,

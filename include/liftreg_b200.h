@@ -114,6 +114,13 @@ LR_API int lr_backproject_forward(const float *proj, const float *poses, int B, 
                                   int d, int w, int h, float *out,
                                   int64_t out_batch_stride, int64_t out_chan_stride, lr_stream_t stream);
 
+/* z-slab form for multi-GPU sharding along axis 0: `out` holds planes [i_begin, i_begin+i_count)
+ * only, i.e. a (B,P,i_count,w,h) tensor with the given strides; projections (<= 1 MB per item) are replicated on
+ * every rank, so the op needs no halo and no collective. */
+LR_API int lr_backproject_forward_slab(const float *proj, const float *poses, int B, int P, int pw, int ph,
+                                       int d_total, int w, int h, int i_begin, int i_count, float *out,
+                                       int64_t out_batch_stride, int64_t out_chan_stride, lr_stream_t stream);
+
 /* adjoint wrt proj; grad_proj (B,P,pw,ph) is ACCUMULATED into (caller zero-initialises). */
 LR_API int lr_backproject_backward(const float *grad_out, int64_t go_batch_stride, int64_t go_chan_stride,
                                    const float *poses, int B, int P, int pw, int ph, int d, int w, int h,
@@ -147,6 +154,17 @@ LR_API int lr_warp_backward(const float *grad_out, const float *img, const float
                             int B, int C, int D, int H, int W,
                             int padding, int mode, int using_scale, int disp_plus_identity,
                             float *grad_img, float *grad_phi, lr_stream_t stream);
+
+/* z-slab forms for multi-GPU sharding along axis 0: phi / out / grad_out / grad_phi are
+ * (B,*,z_count,H,W) tensors holding output planes [z_begin, z_begin+z_count); img (and grad_img) stay the full
+ * (B,C,D,H,W) volume, which every rank holds (16.4 MB at 160^3), so no halo exchange and no reduction is needed. */
+LR_API int lr_warp_forward_slab(const float *img, const float *phi, int B, int C, int D, int H, int W,
+                                int z_begin, int z_count, int padding, int mode, int using_scale,
+                                int disp_plus_identity, float *out, lr_stream_t stream);
+LR_API int lr_warp_backward_slab(const float *grad_out, const float *img, const float *phi,
+                                 int B, int C, int D, int H, int W, int z_begin, int z_count,
+                                 int padding, int mode, int using_scale, int disp_plus_identity,
+                                 float *grad_img, float *grad_phi, lr_stream_t stream);
 
 /* replaces net_utils.py:59-87 identity_map: out (3,D,H,W) */
 LR_API int lr_identity_map(int D, int H, int W, float *out, lr_stream_t stream);

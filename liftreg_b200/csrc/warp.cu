@@ -19,7 +19,10 @@ struct WarpDims {
     int C, D, H, W;
     int nvox;            // D*H*W  (< 2^31: 32-bit voxel offsets; batch/channel offsets are 64-bit)
     int HW;              // H*W
-    unsigned z_magic;    // ceil(2^32 / D): b = (blockIdx.z * z_magic) >> 32 for blockIdx.z < 65536
+    // Output slab (multi-GPU z-slab sharding): phi / out / grad_out / grad_phi hold planes [z_off, z_off+Do) of
+    // axis 0 only, i.e. they are (B,*,Do,H,W) tensors; the image (and grad_img) is always the full (B,C,D,H,W).
+    int Do, z_off, nvox_o;
+    unsigned z_magic;    // ceil(2^32 / Do): b = (blockIdx.z * z_magic) >> 32 for blockIdx.z < 65536
     float hx, hy, hz;    // (W-1)/2, (H-1)/2, (D-1)/2
     float mx, my, mz;    // W-1, H-1, D-1
     double sp0, sp1, sp2;  // 1/(D-1), 1/(H-1), 1/(W-1) as float64 (identity map, net_utils.py:81)
@@ -61,14 +64,14 @@ __global__ void __launch_bounds__(WARP_TX * WARP_TY)
     const int x = blockIdx.x * WARP_TX + threadIdx.x;
     const int y = blockIdx.y * WARP_TY + threadIdx.y;
     const int b = (int)__umulhi(blockIdx.z, g.z_magic);
-    const int z = blockIdx.z - b * g.D;
-    if (IDENT) build_ident_table(ident, g, blockIdx.x * WARP_TX, blockIdx.y * WARP_TY, z);
+    const int z = blockIdx.z - b * g.Do;                       // plane inside the output slab
+    if (IDENT) build_ident_table(ident, g, blockIdx.x * WARP_TX, blockIdx.y * WARP_TY, z + g.z_off);
     if (x >= g.W || y >= g.H) return;
     const int vox = z * g.HW + y * g.W + x;
 
     // channel c of phi addresses volume axis c; grid_sample's x is the last axis (net_utils.py:27-30)
-    const float *phi_b = phi + (int64_t)b * 3 * g.nvox + vox;
-    float gz = ld_stream(phi_b), gy = ld_stream(phi_b + g.nvox), gx = ld_stream(phi_b + 2 * (int64_t)g.nvox);
+    const float *phi_b = phi + (int64_t)b * 3 * g.nvox_o + vox;
+    float gz = ld_stream(phi_b), gy = ld_stream(phi_b + g.nvox_o), gx = ld_stream(phi_b + 2 * (int64_t)g.nvox_o);
     if (IDENT) {  // LiftRegDeformSubspaceBackproj.py:68  deform_field = disp_field + id_transform
         gz = add_rn(gz, ident.z);
         gy = add_rn(gy, ident.y[threadIdx.y]);
@@ -80,7 +83,7 @@ __global__ void __launch_bounds__(WARP_TX * WARP_TY)
 
     const int nchan = C1 ? 1 : g.C;   // C == 1 (the moving CT, label maps) gets a loop-free instantiation
     const float *src = img + (int64_t)b * nchan * g.nvox;
-    float *dst = out + (int64_t)b * nchan * g.nvox + vox;
+    float *dst = out + (int64_t)b * nchan * g.nvox_o + vox;
 
     if (MODE == LR_MODE_NEAREST) {
         const int xn = rint_i(ix), yn = rint_i(iy), zn = rint_i(iz);  // nearbyint: half to even
@@ -93,7 +96,7 @@ __global__ void __launch_bounds__(WARP_TX * WARP_TY)
                 if (SCALE) v = mul_rn(add_rn(v, 1.0f), 0.5f);
             }
             if (SCALE) v = sub_rn(mul_rn(v, 2.0f), 1.0f);
-            st_stream(dst + (int64_t)c * g.nvox, v);
+            st_stream(dst + (int64_t)c * g.nvox_o, v);
         }
         return;
     }
@@ -129,7 +132,7 @@ __global__ void __launch_bounds__(WARP_TX * WARP_TY)
                 acc = add_rn(acc, mul_rn(val, wt[t]));
             }
             if (SCALE) acc = sub_rn(mul_rn(acc, 2.0f), 1.0f);       // net_utils.py:52
-            st_stream(dst + (int64_t)c * g.nvox, acc);
+            st_stream(dst + (int64_t)c * g.nvox_o, acc);
         }
         return;
     }
@@ -153,7 +156,7 @@ __global__ void __launch_bounds__(WARP_TX * WARP_TY)
             }
         }
         if (SCALE) acc = sub_rn(mul_rn(acc, 2.0f), 1.0f);
-        st_stream(dst + (int64_t)c * g.nvox, acc);
+        st_stream(dst + (int64_t)c * g.nvox_o, acc);
     }
 }
 
@@ -168,13 +171,13 @@ __global__ void __launch_bounds__(WARP_TX * WARP_TY)
     const int x = blockIdx.x * WARP_TX + threadIdx.x;
     const int y = blockIdx.y * WARP_TY + threadIdx.y;
     const int b = (int)__umulhi(blockIdx.z, g.z_magic);
-    const int z = blockIdx.z - b * g.D;
-    if (IDENT) build_ident_table(ident, g, blockIdx.x * WARP_TX, blockIdx.y * WARP_TY, z);
+    const int z = blockIdx.z - b * g.Do;
+    if (IDENT) build_ident_table(ident, g, blockIdx.x * WARP_TX, blockIdx.y * WARP_TY, z + g.z_off);
     if (x >= g.W || y >= g.H) return;
     const int vox = z * g.HW + y * g.W + x;
 
-    const float *phi_b = phi + (int64_t)b * 3 * g.nvox + vox;
-    float gz = ld_stream(phi_b), gy = ld_stream(phi_b + g.nvox), gx = ld_stream(phi_b + 2 * (int64_t)g.nvox);
+    const float *phi_b = phi + (int64_t)b * 3 * g.nvox_o + vox;
+    float gz = ld_stream(phi_b), gy = ld_stream(phi_b + g.nvox_o), gx = ld_stream(phi_b + 2 * (int64_t)g.nvox_o);
     if (IDENT) {
         gz = add_rn(gz, ident.z);
         gy = add_rn(gy, ident.y[threadIdx.y]);
@@ -202,7 +205,7 @@ __global__ void __launch_bounds__(WARP_TX * WARP_TY)
     float gix = 0.0f, giy = 0.0f, giz = 0.0f;
     for (int c = 0; c < g.C; ++c) {
         const int64_t chan = ((int64_t)b * g.C + c) * g.nvox;
-        float go = ld_stream(gout + chan + vox);
+        float go = ld_stream(gout + ((int64_t)b * g.C + c) * g.nvox_o + vox);
         if (SCALE) go = mul_rn(go, 2.0f);
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
@@ -228,10 +231,10 @@ __global__ void __launch_bounds__(WARP_TX * WARP_TY)
         }
     }
     if (gphi) {
-        float *gp = gphi + (int64_t)b * 3 * g.nvox + vox;
+        float *gp = gphi + (int64_t)b * 3 * g.nvox_o + vox;
         st_stream(gp, mul_rn(mz, giz));
-        st_stream(gp + g.nvox, mul_rn(my, giy));
-        st_stream(gp + 2 * (int64_t)g.nvox, mul_rn(mx, gix));
+        st_stream(gp + g.nvox_o, mul_rn(my, giy));
+        st_stream(gp + 2 * (int64_t)g.nvox_o, mul_rn(mx, gix));
     }
 }
 
@@ -255,12 +258,15 @@ __global__ void atten_coef_kernel(const float *__restrict__ hu, float *__restric
     }
 }
 
-static WarpDims make_dims(int C, int D, int H, int W) {
+static WarpDims make_dims(int C, int D, int H, int W, int z_begin = 0, int z_count = -1) {
     WarpDims g;
     g.C = C; g.D = D; g.H = H; g.W = W;
     g.nvox = D * H * W;
     g.HW = H * W;
-    g.z_magic = (unsigned)(((1ull << 32) + (unsigned)D - 1) / (unsigned)D);
+    g.Do = z_count < 0 ? D : z_count;
+    g.z_off = z_begin;
+    g.nvox_o = g.Do * H * W;
+    g.z_magic = (unsigned)(((1ull << 32) + (unsigned)g.Do - 1) / (unsigned)g.Do);
     g.hx = (float)(W - 1) / 2.0f; g.hy = (float)(H - 1) / 2.0f; g.hz = (float)(D - 1) / 2.0f;
     g.mx = (float)(W - 1); g.my = (float)(H - 1); g.mz = (float)(D - 1);
     g.sp0 = 1.0 / (double)(D - 1); g.sp1 = 1.0 / (double)(H - 1); g.sp2 = 1.0 / (double)(W - 1);
@@ -318,19 +324,27 @@ static void launch_bwd(bool scale, bool ident, dim3 grid, cudaStream_t st, const
 
 using namespace lr;
 
-extern "C" int lr_warp_forward(const float *img, const float *phi, int B, int C, int D, int H, int W, int padding,
-                               int mode, int using_scale, int disp_plus_identity, float *out, lr_stream_t stream) {
+static int check_slab(int D, int z_begin, int z_count) {
+    LR_REQUIRE(z_begin >= 0 && z_count > 0 && z_begin + z_count <= D, "warp: slab [%d, %d) is not inside [0, %d)", z_begin,
+               z_begin + z_count, D);
+    return LR_OK;
+}
+
+extern "C" int lr_warp_forward_slab(const float *img, const float *phi, int B, int C, int D, int H, int W, int z_begin,
+                                    int z_count, int padding, int mode, int using_scale, int disp_plus_identity,
+                                    float *out, lr_stream_t stream) {
     LR_REQUIRE(img && phi && out, "warp_forward: null pointer");
     if (int e = check_warp_args(B, C, D, H, W, padding, mode)) return e;
-    WarpDims g = make_dims(C, D, H, W);
+    if (int e = check_slab(D, z_begin, z_count)) return e;
+    WarpDims g = make_dims(C, D, H, W, z_begin, z_count);
     cudaStream_t st = as_stream(stream);
     const bool sc = using_scale != 0, id = disp_plus_identity != 0;
-    const int chunk = batch_chunk(D);
+    const int chunk = batch_chunk(g.Do);
     for (int b0 = 0; b0 < B; b0 += chunk) {
         const int nb = B - b0 < chunk ? B - b0 : chunk;
-        const dim3 grid = warp_grid(nb, D, H, W);
-        const float *im = img + (int64_t)b0 * C * g.nvox, *ph = phi + (int64_t)b0 * 3 * g.nvox;
-        float *o = out + (int64_t)b0 * C * g.nvox;
+        const dim3 grid = warp_grid(nb, g.Do, H, W);
+        const float *im = img + (int64_t)b0 * C * g.nvox, *ph = phi + (int64_t)b0 * 3 * g.nvox_o;
+        float *o = out + (int64_t)b0 * C * g.nvox_o;
         if (padding == LR_PAD_ZEROS) {
             if (mode == LR_MODE_LINEAR) launch_fwd<LR_PAD_ZEROS, LR_MODE_LINEAR>(sc, id, grid, st, im, ph, o, g);
             else launch_fwd<LR_PAD_ZEROS, LR_MODE_NEAREST>(sc, id, grid, st, im, ph, o, g);
@@ -343,35 +357,48 @@ extern "C" int lr_warp_forward(const float *img, const float *phi, int B, int C,
     return LR_OK;
 }
 
-extern "C" int lr_warp_backward(const float *grad_out, const float *img, const float *phi, int B, int C, int D, int H,
-                                int W, int padding, int mode, int using_scale, int disp_plus_identity, float *grad_img,
-                                float *grad_phi, lr_stream_t stream) {
+extern "C" int lr_warp_forward(const float *img, const float *phi, int B, int C, int D, int H, int W, int padding,
+                               int mode, int using_scale, int disp_plus_identity, float *out, lr_stream_t stream) {
+    return lr_warp_forward_slab(img, phi, B, C, D, H, W, 0, D, padding, mode, using_scale, disp_plus_identity, out, stream);
+}
+
+extern "C" int lr_warp_backward_slab(const float *grad_out, const float *img, const float *phi, int B, int C, int D, int H,
+                                     int W, int z_begin, int z_count, int padding, int mode, int using_scale,
+                                     int disp_plus_identity, float *grad_img, float *grad_phi, lr_stream_t stream) {
     LR_REQUIRE(grad_out && img && phi, "warp_backward: null pointer");
     if (int e = check_warp_args(B, C, D, H, W, padding, mode)) return e;
+    if (int e = check_slab(D, z_begin, z_count)) return e;
     if (!grad_img && !grad_phi) return LR_OK;
     cudaStream_t st = as_stream(stream);
-    WarpDims g = make_dims(C, D, H, W);
+    WarpDims g = make_dims(C, D, H, W, z_begin, z_count);
     if (mode == LR_MODE_NEAREST) {
         // nearest sampling is piecewise constant in phi: zero grid gradient (ATen does the same); the image
         // gradient is a pure scatter, which the linear kernel cannot express -> not needed by the reference
         // (evaluate_dir_lab.py:221 warps label maps without autograd).
         LR_REQUIRE(!grad_img, "warp_backward: grad_img is not supported for nearest mode");
-        cudaError_t ce = cudaMemsetAsync(grad_phi, 0, sizeof(float) * 3 * (size_t)B * g.nvox, st);
+        cudaError_t ce = cudaMemsetAsync(grad_phi, 0, sizeof(float) * 3 * (size_t)B * g.nvox_o, st);
         if (ce != cudaSuccess) { set_error("warp_backward: memset failed: %s", cudaGetErrorString(ce)); return LR_ERR_CUDA; }
         return LR_OK;
     }
     const bool sc = using_scale != 0, id = disp_plus_identity != 0;
-    const int chunk = batch_chunk(D);
+    const int chunk = batch_chunk(g.Do);
     for (int b0 = 0; b0 < B; b0 += chunk) {
         const int nb = B - b0 < chunk ? B - b0 : chunk;
-        const dim3 grid = warp_grid(nb, D, H, W);
-        const int64_t io = (int64_t)b0 * C * g.nvox, po = (int64_t)b0 * 3 * g.nvox;
+        const dim3 grid = warp_grid(nb, g.Do, H, W);
+        const int64_t io = (int64_t)b0 * C * g.nvox, oo = (int64_t)b0 * C * g.nvox_o, po = (int64_t)b0 * 3 * g.nvox_o;
         float *gi = grad_img ? grad_img + io : nullptr, *gp = grad_phi ? grad_phi + po : nullptr;
-        if (padding == LR_PAD_ZEROS) launch_bwd<LR_PAD_ZEROS>(sc, id, grid, st, grad_out + io, img + io, phi + po, gi, gp, g);
-        else launch_bwd<LR_PAD_BORDER>(sc, id, grid, st, grad_out + io, img + io, phi + po, gi, gp, g);
+        if (padding == LR_PAD_ZEROS) launch_bwd<LR_PAD_ZEROS>(sc, id, grid, st, grad_out + oo, img + io, phi + po, gi, gp, g);
+        else launch_bwd<LR_PAD_BORDER>(sc, id, grid, st, grad_out + oo, img + io, phi + po, gi, gp, g);
         if (int e = check_launch("warp_backward_kernel")) return e;
     }
     return LR_OK;
+}
+
+extern "C" int lr_warp_backward(const float *grad_out, const float *img, const float *phi, int B, int C, int D, int H,
+                                int W, int padding, int mode, int using_scale, int disp_plus_identity, float *grad_img,
+                                float *grad_phi, lr_stream_t stream) {
+    return lr_warp_backward_slab(grad_out, img, phi, B, C, D, H, W, 0, D, padding, mode, using_scale, disp_plus_identity,
+                                 grad_img, grad_phi, stream);
 }
 
 extern "C" int lr_identity_map(int D, int H, int W, float *out, lr_stream_t stream) {

@@ -137,9 +137,10 @@ def project_grid(poses, resolution, obj_shape, spacing, device, y_norm_mode=YNOR
 # --------------------------------------------------------------------------- backprojection
 class _Backproject(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, proj, poses, d, w, h, out, channel_offset):
+    def forward(ctx, proj, poses, d_total, w, h, out, channel_offset, i_begin, i_count):
         proj = _need_cuda_f32(proj, "target_proj")
         B, P, pw, ph = proj.shape
+        d = i_count
         nv = d * w * h
         if out is None:
             out = torch.empty((B, P, d, w, h), device=proj.device, dtype=torch.float32)
@@ -153,15 +154,19 @@ class _Backproject(torch.autograd.Function):
             view, bs, cs = out[:, channel_offset:channel_offset + P], out.shape[1] * nv, nv
             ctx.mark_dirty(out)
         with torch.cuda.device(proj.device):
-            _native.check(_native.lib().lr_backproject_forward(_ptr(proj), _fp(poses), B, P, pw, ph, d, w, h,
-                                                               ctypes.c_void_p(view.data_ptr()), bs, cs, _stream()),
-                          "lr_backproject_forward")
-        ctx.geom = (poses, B, P, pw, ph, d, w, h, channel_offset, out.shape[1])
+            _native.check(_native.lib().lr_backproject_forward_slab(_ptr(proj), _fp(poses), B, P, pw, ph, d_total, w, h,
+                                                                    i_begin, i_count, ctypes.c_void_p(view.data_ptr()),
+                                                                    bs, cs, _stream()),
+                          "lr_backproject_forward_slab")
+        ctx.geom = (poses, B, P, pw, ph, d, w, h, channel_offset, out.shape[1], d_total, i_begin)
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        poses, B, P, pw, ph, d, w, h, off, nchan = ctx.geom
+        poses, B, P, pw, ph, d, w, h, off, nchan, d_total, i_begin = ctx.geom
+        if d != d_total:
+            raise NotImplementedError("gradient wrt the projections is not implemented for slab-sharded backprojection "
+                                      "(the reference detaches this output, LiftRegDeformSubspaceBackproj.py:93)")
         grad_out = _need_cuda_f32(grad_out, "grad_out")
         nv = d * w * h
         gview = grad_out[:, off:off + P]
@@ -170,16 +175,18 @@ class _Backproject(torch.autograd.Function):
             _native.check(_native.lib().lr_backproject_backward(ctypes.c_void_p(gview.data_ptr()), nchan * nv, nv, _fp(poses),
                                                                 B, P, pw, ph, d, w, h, _ptr(grad_proj), _stream()),
                           "lr_backproject_backward")
-        return grad_proj, None, None, None, None, None, None
+        return grad_proj, None, None, None, None, None, None, None, None
 
 
-def backproject(target_proj, poses, img_shape, out=None, channel_offset=0):
+def backproject(target_proj, poses, img_shape, out=None, channel_offset=0, slab=None):
     """Lift projections (B,P,pw,ph) into a volume (B,P,d,w,h); differentiable wrt target_proj.
 
     Replaces reference sdct:227-250 + LiftRegDeformSubspaceBackproj.py:85-93 in one kernel (no 131 MB grid).
     poses: (P,3) or (B,P,3) float32 (item 0 is used, as the reference freezes geometry from the first batch).
     out/channel_offset: optionally write into channels [offset, offset+P) of a pre-allocated (B,Ctot,d,w,h)
     buffer, which removes the torch.cat of model :95-98; the whole buffer is returned.
+    slab=(i_begin, i_count): compute only planes [i_begin, i_begin+i_count) of axis 0 (multi-GPU z-slab sharding);
+    the result (and `out`) then has i_count planes.
     """
     if target_proj.dim() != 4:
         raise ValueError("target_proj must be (B,P,pw,ph), got %s" % (tuple(target_proj.shape),))
@@ -187,7 +194,10 @@ def backproject(target_proj, poses, img_shape, out=None, channel_offset=0):
     if poses.shape[0] != target_proj.shape[1]:
         raise ValueError("poses has %d views but target_proj has %d" % (poses.shape[0], target_proj.shape[1]))
     d, w, h = (int(s) for s in img_shape)
-    return _Backproject.apply(target_proj, poses, d, w, h, out, int(channel_offset))
+    i_begin, i_count = (0, d) if slab is None else (int(slab[0]), int(slab[1]))
+    if not (0 <= i_begin and i_count > 0 and i_begin + i_count <= d):
+        raise ValueError("slab %r is not inside [0, %d)" % (slab, d))
+    return _Backproject.apply(target_proj, poses, d, w, h, out, int(channel_offset), i_begin, i_count)
 
 
 def backproj_grid(poses, img_shape, proj_shape, device):
@@ -208,51 +218,64 @@ def backproj_grid(poses, img_shape, proj_shape, device):
 # --------------------------------------------------------------------------- warp
 class _Warp(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, img, phi, padding, mode, using_scale, disp_plus_identity):
+    def forward(ctx, img, phi, padding, mode, using_scale, disp_plus_identity, z_begin):
         img = _need_cuda_f32(img, "input1")
         phi = _need_cuda_f32(phi, "input2")
         B, C, D, H, W = img.shape
-        out = torch.empty_like(img)
+        z_count = phi.shape[2]
+        out = torch.empty((B, C, z_count, H, W), device=img.device, dtype=torch.float32)
         with torch.cuda.device(img.device):
-            _native.check(_native.lib().lr_warp_forward(_ptr(img), _ptr(phi), B, C, D, H, W, padding, mode,
-                                                        int(using_scale), int(disp_plus_identity), _ptr(out), _stream()),
-                          "lr_warp_forward")
+            _native.check(_native.lib().lr_warp_forward_slab(_ptr(img), _ptr(phi), B, C, D, H, W, z_begin, z_count, padding,
+                                                             mode, int(using_scale), int(disp_plus_identity), _ptr(out),
+                                                             _stream()),
+                          "lr_warp_forward_slab")
         ctx.save_for_backward(img, phi)
-        ctx.cfg = (padding, mode, using_scale, disp_plus_identity)
+        ctx.cfg = (padding, mode, using_scale, disp_plus_identity, z_begin)
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
         img, phi = ctx.saved_tensors
-        padding, mode, using_scale, ident = ctx.cfg
+        padding, mode, using_scale, ident, z_begin = ctx.cfg
         grad_out = _need_cuda_f32(grad_out, "grad_out")
         B, C, D, H, W = img.shape
+        z_count = phi.shape[2]
         need_img, need_phi = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         if need_img and mode == MODE_NEAREST:
             raise NotImplementedError("gradient wrt the image is not implemented for nearest-mode warps")
         gimg = torch.zeros_like(img) if need_img else None
         gphi = torch.empty_like(phi) if need_phi else None
         with torch.cuda.device(img.device):
-            _native.check(_native.lib().lr_warp_backward(_ptr(grad_out), _ptr(img), _ptr(phi), B, C, D, H, W, padding, mode,
-                                                         int(using_scale), int(ident), _ptr(gimg), _ptr(gphi), _stream()),
-                          "lr_warp_backward")
-        return gimg, gphi, None, None, None, None
+            _native.check(_native.lib().lr_warp_backward_slab(_ptr(grad_out), _ptr(img), _ptr(phi), B, C, D, H, W, z_begin,
+                                                              z_count, padding, mode, int(using_scale), int(ident),
+                                                              _ptr(gimg), _ptr(gphi), _stream()),
+                          "lr_warp_backward_slab")
+        return gimg, gphi, None, None, None, None, None
 
 
-def warp(img, phi, zero_boundary=False, using_scale=True, mode="bilinear", disp_plus_identity=False):
+def warp(img, phi, zero_boundary=False, using_scale=True, mode="bilinear", disp_plus_identity=False, z_begin=None):
     """Spatial transformer: img (B,C,D,H,W) sampled at phi (B,3,D,H,W) in [-1,1]; differentiable wrt both.
 
     Replaces reference net_utils.py:26-56.  disp_plus_identity=True treats phi as a displacement and adds the
     identity map in-kernel (fuses LiftRegDeformSubspaceBackproj.py:68).
+    z_begin: phi is a z-slab (B,3,Dz,H,W) holding output planes [z_begin, z_begin+Dz) of the full (D,H,W) image
+    (multi-GPU z-slab sharding); the result is the matching (B,C,Dz,H,W) slab.
     """
     if mode not in ("bilinear", "nearest"):
         raise ValueError("mode must be 'bilinear' or 'nearest', got %r" % (mode,))
     if img.dim() != 5 or phi.dim() != 5 or phi.shape[1] != 3 or phi.shape[0] != img.shape[0] \
-            or tuple(phi.shape[2:]) != tuple(img.shape[2:]):
+            or tuple(phi.shape[3:]) != tuple(img.shape[3:]):
         raise ValueError("expected input1 (B,C,D,H,W) and input2 (B,3,D,H,W); got %s and %s"
                          % (tuple(img.shape), tuple(phi.shape)))
+    if z_begin is None:
+        if phi.shape[2] != img.shape[2]:
+            raise ValueError("input2 has %d planes but input1 has %d (pass z_begin for a slab)" % (phi.shape[2], img.shape[2]))
+        z_begin = 0
+    if not (0 <= z_begin and z_begin + phi.shape[2] <= img.shape[2]):
+        raise ValueError("slab [%d, %d) is not inside [0, %d)" % (z_begin, z_begin + phi.shape[2], img.shape[2]))
     return _Warp.apply(img, phi, PAD_ZEROS if zero_boundary else PAD_BORDER,
-                       MODE_LINEAR if mode == "bilinear" else MODE_NEAREST, bool(using_scale), bool(disp_plus_identity))
+                       MODE_LINEAR if mode == "bilinear" else MODE_NEAREST, bool(using_scale), bool(disp_plus_identity),
+                       int(z_begin))
 
 
 def identity_map(sz, device):

@@ -1,0 +1,143 @@
+"""Multi-GPU partitioning of the resampling path on one 8xB200 box.
+
+One process per GPU (`torch.distributed`, NCCL over NVLink/NVSwitch on the GPU box, gloo in the CPU tests):
+
+  * DRR forward      every ray is independent and needs the whole volume: the (batch x view) list is split across
+                     ranks, the volume is replicated, and the detector images are all-gathered (0.9 MB at cfg 1,
+                     67 MB at cfg 4: latency-bound).  Each rank's kernel writes straight into its slot of the
+                     gather buffer, so the collective is the only copy.
+  * backprojection   per-voxel gather from tiny, replicated projections: split the output along axis 0 (z-slabs);
+                     no halo, no collective (the output stays sharded for the data-parallel consumer).
+  * warp             split the OUTPUT along axis 0; phi is sharded like the output, the moving image is replicated
+                     (16.4 MB at 160^3), so displaced samples may land anywhere without a halo exchange.
+
+The reference has no multi-GPU code at all (main.py:108-110 picks one device); this is new functionality required by
+BASELINE.json's north star, not a port.  Partition arithmetic is pure Python and is exercised on CPU with
+world_size-2 gloo process groups (tests/test_sharding_gloo.py) by injecting the oracle as the compute function.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def split_range(n, world, rank):
+    """Balanced contiguous partition of range(n): returns (start, stop) of `rank`; the first n % world ranks get one
+    extra item.  Ranks beyond n get an empty range."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError("bad world/rank %r/%r" % (world, rank))
+    base, extra = divmod(int(n), world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def all_ranges(n, world):
+    return [split_range(n, world, r) for r in range(world)]
+
+
+def _world(group):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(group), dist.get_rank(group)
+    return 1, 0
+
+
+# --------------------------------------------------------------------------------------------- DRR: view sharding
+def drr_project_sharded(vol, poses, resolution, spacing, y_norm_mode=0, out_scale=0.1, group=None, gather=True,
+                        project_fn=None):
+    """View-sharded DRR.  vol (B,d,w,h) replicated on every rank; poses (P,3) or (B,P,3).
+
+    The flattened list of (b,p) views is split contiguously across ranks; each rank projects its views and, if
+    `gather`, the detector images are all-gathered so every rank returns the full (B,P,rd,rh).  With gather=False
+    the rank's own (n_local,rd,rh) images are returned together with its (start, stop) range.
+    `project_fn(vol_b (1,d,w,h), poses (n,3), resolution, spacing, y_norm_mode, out_scale) -> (1,n,rd,rh)` defaults
+    to the CUDA op; the CPU tests inject the oracle.
+    """
+    if project_fn is None:
+        from . import ops
+        project_fn = ops.drr_project
+    world, rank = _world(group)
+    B = vol.shape[0]
+    p64 = np.ascontiguousarray(poses, dtype=np.float64)
+    if p64.ndim == 2:
+        p64 = np.broadcast_to(p64[None], (B,) + p64.shape)
+    P = p64.shape[1]
+    rd, rh = int(resolution[0]), int(resolution[1])
+    n_views = B * P
+    ranges = all_ranges(n_views, world)
+    v0, v1 = ranges[rank]
+    slot = max(hi - lo for lo, hi in ranges)              # all_gather needs equal-sized contributions
+    buf = torch.zeros((world, slot, rd, rh), device=vol.device, dtype=torch.float32)
+    mine = buf[rank]
+    v = v0
+    while v < v1:                                          # one call per batch item touched by [v0, v1)
+        b, p = divmod(v, P)
+        p_hi = min(P, p + (v1 - v))
+        out = project_fn(vol[b:b + 1], p64[b, p:p_hi], (rd, rh), spacing, y_norm_mode, out_scale)
+        mine[v - v0:v - v0 + (p_hi - p)].copy_(out[0])
+        v += p_hi - p
+    if not gather:
+        return mine[:v1 - v0], (v0, v1)
+    if world > 1:
+        # NCCL gathers in place (the send slice already sits in the receive buffer); gloo wants a separate input
+        send = mine.reshape(-1) if buf.is_cuda else mine.reshape(-1).clone()
+        dist.all_gather_into_tensor(buf.view(-1), send, group=group)
+    full = torch.cat([buf[r, :hi - lo] for r, (lo, hi) in enumerate(ranges)], dim=0)
+    return full.reshape(B, P, rd, rh)
+
+
+# --------------------------------------------------------------------------------------------- z-slab sharding
+def backproject_sharded(target_proj, poses, img_shape, group=None, gather=False, backproject_fn=None):
+    """z-slab-sharded backprojection.  target_proj (B,P,pw,ph) and poses replicated; returns this rank's slab
+    (B,P,nz,w,h) and its (z_begin, z_end), or the full volume if gather=True (all-gather along axis 2).
+    No halo and no reduction: a voxel's value depends only on the (replicated) projections."""
+    if backproject_fn is None:
+        from . import ops
+        backproject_fn = lambda tp, ps, shp, slab: ops.backproject(tp, ps, shp, slab=slab)   # noqa: E731
+    world, rank = _world(group)
+    d = int(img_shape[0])
+    z0, z1 = split_range(d, world, rank)
+    slab = backproject_fn(target_proj, poses, img_shape, (z0, z1 - z0)) if z1 > z0 else \
+        torch.empty((target_proj.shape[0], target_proj.shape[1], 0, int(img_shape[1]), int(img_shape[2])),
+                    device=target_proj.device)
+    if not gather:
+        return slab, (z0, z1)
+    return _gather_slabs(slab, d, 2, world, group), (0, d)
+
+
+def warp_sharded(img, phi_slab, z_range, zero_boundary=False, using_scale=True, mode="bilinear",
+                 disp_plus_identity=False, group=None, gather=False, warp_fn=None):
+    """z-slab-sharded warp.  img (B,C,D,H,W) replicated; phi_slab (B,3,nz,H,W) = this rank's planes
+    [z_range[0], z_range[1]) of the map (or of the displacement if disp_plus_identity).  Returns the matching output
+    slab, or the full volume if gather=True.  Differentiable wrt phi_slab; a gradient wrt img would be a partial
+    sum that the caller must all-reduce."""
+    if warp_fn is None:
+        from . import ops
+        warp_fn = lambda a, b, z: ops.warp(a, b, zero_boundary=zero_boundary, using_scale=using_scale, mode=mode,  # noqa: E731
+                                           disp_plus_identity=disp_plus_identity, z_begin=z)
+    world, rank = _world(group)
+    z0, z1 = int(z_range[0]), int(z_range[1])
+    if phi_slab.shape[2] != z1 - z0:
+        raise ValueError("phi_slab has %d planes, z_range says %d" % (phi_slab.shape[2], z1 - z0))
+    out = warp_fn(img, phi_slab, z0)
+    if not gather:
+        return out
+    return _gather_slabs(out, img.shape[2], 2, world, group)
+
+
+def shard_along_z(full, world, rank, dim=2):
+    """This rank's contiguous slab of `full` along `dim` (what a data loader would hand the rank) and its range."""
+    z0, z1 = split_range(full.shape[dim], world, rank)
+    return full.narrow(dim, z0, z1 - z0).contiguous(), (z0, z1)
+
+
+def _gather_slabs(slab, d, dim, world, group):
+    if world == 1:
+        return slab
+    ranges = all_ranges(d, world)
+    width = max(hi - lo for lo, hi in ranges)
+    pad_shape = list(slab.shape)
+    pad_shape[dim] = width
+    padded = torch.zeros(pad_shape, device=slab.device, dtype=slab.dtype)
+    padded.narrow(dim, 0, slab.shape[dim]).copy_(slab)
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded, group=group)
+    return torch.cat([parts[r].narrow(dim, 0, hi - lo) for r, (lo, hi) in enumerate(ranges)], dim=dim)
