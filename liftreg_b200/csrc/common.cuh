@@ -55,6 +55,63 @@ __device__ __forceinline__ float clamp_index(float x, float hi) {   // keep |x| 
     return fminf(fmaxf(x, -2.0f), hi);
 }
 
+// ---- packed fp32x2 arithmetic (Blackwell: FADD2 / FMUL2 / FFMA2 issue two IEEE-rounded fp32 ops per slot) -----
+// The resampling kernels are bound by instruction issue, not by the FMA pipe, so each thread processes TWO
+// independent outputs and runs their (identical) fp32 op sequences as one packed sequence.  Every lane of a
+// packed op is rounded exactly like the scalar op (.rn), so bit-exactness against the reference is unaffected.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 a, float &lo, float &hi) {
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a));
+}
+__device__ __forceinline__ f32x2 splat2(float v) { return pack2(v, v); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+// packed floor for two values already known to lie in [0, 2^22): float floors and int floors
+__device__ __forceinline__ void floor2_fi(f32x2 x, f32x2 &f, int &i_lo, int &i_hi) {
+    const f32x2 M = splat2(12582912.0f);
+    const f32x2 t = add2(x, M);
+    const f32x2 r = sub2(t, M);
+    float xl, xh, rl, rh, tl, th;
+    unpack2(x, xl, xh);
+    unpack2(r, rl, rh);
+    unpack2(t, tl, th);
+    const bool ul = rl > xl, uh = rh > xh;
+    f = pack2(ul ? __fsub_rn(rl, 1.0f) : rl, uh ? __fsub_rn(rh, 1.0f) : rh);
+    i_lo = __float_as_int(tl) - 0x4B400000 - (ul ? 1 : 0);
+    i_hi = __float_as_int(th) - 0x4B400000 - (uh ? 1 : 0);
+}
+
+// Hides how a pointer was computed so that nvcc keeps it in a register pair instead of re-deriving it (as a 64-bit
+// multiply-add chain) at every use: `opaque(base) + u32_index` then costs a single IMAD.WIDE.U32.
+template <typename T>
+__device__ __forceinline__ T *opaque(T *p) {
+    asm volatile("" : "+l"(p));
+    return p;
+}
+
 // Streaming (read-once / write-once) accesses: keep them out of L1 so the gather working set stays resident.
 __device__ __forceinline__ float ld_stream(const float *p) {
     float v;

@@ -78,44 +78,53 @@ struct Sample {
     float iz, iy, ix;  // source indices along volume axes 0 (d), 1 (w), 2 (h)
 };
 
-// sdct:50-56 + flip (:76) + ATen unnormalise
-__device__ __forceinline__ Sample ray_point(const Ray &r, const DrrDims &g, int j) {
-    const float T = mul_rn(r.r2, sub_rn((float)j, r.sy));
+// sdct:50-56 + flip (:76) + ATen unnormalise.  jf = (float)j is carried as a float counter (no I2F).
+__device__ __forceinline__ Sample ray_point(const Ray &r, const DrrDims &g, float jf) {
+    const float T = mul_rn(r.r2, sub_rn(jf, r.sy));
     const float X = add_rn(mul_rn(r.Dx, T), r.sx), Y = add_rn(mul_rn(r.Dy, T), r.sy), Z = add_rn(mul_rn(r.Dz, T), r.sz);
     const float g0 = div_const(X, g.div_x);                  // X/d*2
     const float g1 = add_rn(div_const(Y, g.div_y), -1.0f);   // Y/(w-1)*2 + -1
     const float g2 = div_const(Z, g.div_z);                  // Z/h*2
     Sample s;
-    s.iz = mul_rn(add_rn(g0, 1.0f), g.hd);
-    s.iy = mul_rn(add_rn(g1, 1.0f), g.hw);
-    s.ix = mul_rn(add_rn(g2, 1.0f), g.hh);
+    // beyond [-2, S+1] no tap is in bounds; the clamp keeps floor_fi's |x| < 2^22 precondition
+    s.iz = clamp_index(mul_rn(add_rn(g0, 1.0f), g.hd), g.hd * 2.0f + 2.0f);
+    s.iy = clamp_index(mul_rn(add_rn(g1, 1.0f), g.hw), g.hw * 2.0f + 2.0f);
+    s.ix = clamp_index(mul_rn(add_rn(g2, 1.0f), g.hh), g.hh * 2.0f + 2.0f);
     return s;
 }
 
 struct Taps {
-    float wt[8];
-    int64_t base;
-    unsigned okmask;
+    float wt[8];      // ATen order: tnw tne tsw tse bnw bne bsw bse (x fastest, then y, then z)
+    int base;         // voxel offset of tap (z0,y0,x0); < 2^31 (checked on the host)
+    int x0, y0, z0;
 };
 
 __device__ __forceinline__ Taps make_taps(const Sample &s, const DrrDims &g) {
-    const float fx = floorf(s.ix), fy = floorf(s.iy), fz = floorf(s.iz);
-    const int x0 = __float2int_rd(s.ix), y0 = __float2int_rd(s.iy), z0 = __float2int_rd(s.iz);
+    float fx, fy, fz;
+    Taps t;
+    floor_fi(s.ix, fx, t.x0);
+    floor_fi(s.iy, fy, t.y0);
+    floor_fi(s.iz, fz, t.z0);
     const float wx1 = sub_rn(s.ix, fx), wx0 = sub_rn(add_rn(fx, 1.0f), s.ix);
     const float wy1 = sub_rn(s.iy, fy), wy0 = sub_rn(add_rn(fy, 1.0f), s.iy);
     const float wz1 = sub_rn(s.iz, fz), wz0 = sub_rn(add_rn(fz, 1.0f), s.iz);
     const float a00 = mul_rn(wx0, wy0), a10 = mul_rn(wx1, wy0), a01 = mul_rn(wx0, wy1), a11 = mul_rn(wx1, wy1);
-    Taps t;
     t.wt[0] = mul_rn(a00, wz0); t.wt[1] = mul_rn(a10, wz0); t.wt[2] = mul_rn(a01, wz0); t.wt[3] = mul_rn(a11, wz0);
     t.wt[4] = mul_rn(a00, wz1); t.wt[5] = mul_rn(a10, wz1); t.wt[6] = mul_rn(a01, wz1); t.wt[7] = mul_rn(a11, wz1);
-    const unsigned vx0 = (unsigned)x0 < (unsigned)g.h, vx1 = (unsigned)(x0 + 1) < (unsigned)g.h;
-    const unsigned vy0 = (unsigned)y0 < (unsigned)g.w, vy1 = (unsigned)(y0 + 1) < (unsigned)g.w;
-    const unsigned vz0 = (unsigned)z0 < (unsigned)g.d, vz1 = (unsigned)(z0 + 1) < (unsigned)g.d;
-    const unsigned mx = vx0 | (vx1 << 1);                 // bits for tx = 0,1
-    const unsigned mxy = (vy0 ? mx : 0u) | ((vy1 ? mx : 0u) << 2);
-    t.okmask = (vz0 ? mxy : 0u) | ((vz1 ? mxy : 0u) << 4);
-    t.base = ((int64_t)z0 * g.w + y0) * g.h + x0;
+    t.base = (t.z0 * g.w + t.y0) * g.h + t.x0;
     return t;
+}
+
+__device__ __forceinline__ bool taps_interior(const Taps &t, const DrrDims &g) {   // all 8 taps inside the volume
+    return (unsigned)t.x0 < (unsigned)(g.h - 1) && (unsigned)t.y0 < (unsigned)(g.w - 1) && (unsigned)t.z0 < (unsigned)(g.d - 1);
+}
+__device__ __forceinline__ unsigned taps_mask(const Taps &t, const DrrDims &g) {   // bit c set <=> tap c inside
+    const unsigned vx0 = (unsigned)t.x0 < (unsigned)g.h, vx1 = (unsigned)(t.x0 + 1) < (unsigned)g.h;
+    const unsigned vy0 = (unsigned)t.y0 < (unsigned)g.w, vy1 = (unsigned)(t.y0 + 1) < (unsigned)g.w;
+    const unsigned vz0 = (unsigned)t.z0 < (unsigned)g.d, vz1 = (unsigned)(t.z0 + 1) < (unsigned)g.d;
+    const unsigned mx = vx0 | (vx1 << 1);
+    const unsigned mxy = (vy0 ? mx : 0u) | ((vy1 ? mx : 0u) << 2);
+    return (vz0 ? mxy : 0u) | ((vz1 ? mxy : 0u) << 4);
 }
 
 __global__ void __launch_bounds__(32 * DRR_ROWS)
@@ -126,28 +135,37 @@ __global__ void __launch_bounds__(32 * DRR_ROWS)
     const DrrView vw = views.v[blockIdx.z];
     const Ray r = ray_setup(vw, g, u, v);
     const float *V = vol + (int64_t)vw.vol * g.nvox;
-    const int64_t sy = g.h, sz = (int64_t)g.w * g.h;
+    const int sy = g.h, sz = g.w * g.h;
 
     float acc = 0.0f;
-    for (int j = r.j0; j <= r.j1; ++j) {
-        const Sample s = ray_point(r, g, j);
+    float jf = (float)r.j0;
+    for (int j = r.j0; j <= r.j1; ++j, jf += 1.0f) {
+        const Sample s = ray_point(r, g, jf);
         const Taps t = make_taps(s, g);
-        if (t.okmask == 0u) continue;
         const float *b = V + t.base;
-        float val[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const int64_t off = (c & 1) + ((c >> 1) & 1) * sy + (c >> 2) * sz;
-            val[c] = (t.okmask >> c) & 1u ? __ldg(b + off) : 0.0f;
-        }
         float o = 0.0f;
+        if (taps_interior(t, g)) {
+            const float *b1 = b + sy, *b2 = b + sz, *b3 = b2 + sy;
+            const float v0 = __ldg(b), v1 = __ldg(b + 1), v2 = __ldg(b1), v3 = __ldg(b1 + 1);
+            const float v4 = __ldg(b2), v5 = __ldg(b2 + 1), v6 = __ldg(b3), v7 = __ldg(b3 + 1);
+            // ATen: out += val*w per tap, separately rounded, in tap order
+            o = add_rn(o, mul_rn(v0, t.wt[0])); o = add_rn(o, mul_rn(v1, t.wt[1]));
+            o = add_rn(o, mul_rn(v2, t.wt[2])); o = add_rn(o, mul_rn(v3, t.wt[3]));
+            o = add_rn(o, mul_rn(v4, t.wt[4])); o = add_rn(o, mul_rn(v5, t.wt[5]));
+            o = add_rn(o, mul_rn(v6, t.wt[6])); o = add_rn(o, mul_rn(v7, t.wt[7]));
+        } else {
+            const unsigned m = taps_mask(t, g);
+            if (m == 0u) continue;                                  // contributes exactly +0
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
-            if ((t.okmask >> c) & 1u) o = add_rn(o, mul_rn(val[c], t.wt[c]));   // ATen: out += val*w, no fma
-        acc = add_rn(acc, o);                                                   // sum over the ray (sdct:81)
+            for (int c = 0; c < 8; ++c) {
+                const int off = (c & 1) + ((c >> 1) & 1) * sy + (c >> 2) * sz;
+                if ((m >> c) & 1u) o = add_rn(o, mul_rn(__ldg(b + off), t.wt[c]));
+            }
+        }
+        acc = add_rn(acc, o);                                       // sum over the ray (sdct:81), j ascending
     }
-    float o = mul_rn(acc, r.dx);                                                // * dx (sdct:81)
-    if (g.out_scale != 1.0f) o = mul_rn(o, g.out_scale);                        // *= 0.1 (sdct:85)
+    float o = mul_rn(acc, r.dx);                                    // * dx (sdct:81)
+    if (g.out_scale != 1.0f) o = mul_rn(o, g.out_scale);            // *= 0.1 (sdct:85)
     proj[((int64_t)(g.view0 + blockIdx.z) * g.rd + u) * g.rh + v] = o;
 }
 
@@ -160,20 +178,22 @@ __global__ void __launch_bounds__(32 * DRR_ROWS)
     const DrrView vw = views.v[blockIdx.z];
     const Ray r = ray_setup(vw, g, u, v);
     float *V = gvol + (int64_t)vw.vol * g.nvox;
-    const int64_t sy = g.h, sz = (int64_t)g.w * g.h;
+    const int sy = g.h, sz = g.w * g.h;
     float go = gproj[((int64_t)(g.view0 + blockIdx.z) * g.rd + u) * g.rh + v];
     if (g.out_scale != 1.0f) go = mul_rn(go, g.out_scale);
     const float gs = mul_rn(go, r.dx);
     if (gs == 0.0f) return;
-    for (int j = r.j0; j <= r.j1; ++j) {
-        const Sample s = ray_point(r, g, j);
+    float jf = (float)r.j0;
+    for (int j = r.j0; j <= r.j1; ++j, jf += 1.0f) {
+        const Sample s = ray_point(r, g, jf);
         const Taps t = make_taps(s, g);
-        if (t.okmask == 0u) continue;
+        const unsigned m = taps_mask(t, g);
+        if (m == 0u) continue;
         float *b = V + t.base;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-            const int64_t off = (c & 1) + ((c >> 1) & 1) * sy + (c >> 2) * sz;
-            if ((t.okmask >> c) & 1u) red_add(b + off, mul_rn(t.wt[c], gs));
+            const int off = (c & 1) + ((c >> 1) & 1) * sy + (c >> 2) * sz;
+            if ((m >> c) & 1u) red_add(b + off, mul_rn(t.wt[c], gs));
         }
     }
 }
@@ -206,6 +226,7 @@ static int fill_dims(DrrDims &g, int B, int d, int w, int h, int n_pose_sets, in
     LR_REQUIRE(y_norm_mode == LR_YNORM_WM1 || y_norm_mode == LR_YNORM_W, "drr: y_norm_mode must be 0 or 1");
     LR_REQUIRE(spacing != nullptr, "drr: spacing is null");
     LR_REQUIRE((rd + DRR_ROWS - 1) / DRR_ROWS <= 65535, "drr: detector too tall for the launch grid");
+    LR_REQUIRE((int64_t)d * w * h < (1ll << 31) - 2ll * w * h - 4, "drr: d*w*h must fit 32-bit voxel offsets");
     g.d = d; g.w = w; g.h = h; g.rd = rd; g.rh = rh; g.view0 = 0;
     g.half_rd = (float)((double)rd / 2.0); g.half_rh = (float)((double)rh / 2.0);
     g.sp0 = spacing[0]; g.sp1 = spacing[1]; g.sp2 = spacing[2];

@@ -13,7 +13,9 @@
 namespace lr {
 
 constexpr int WARP_TX = 32;   // threads along W (coalesced 128 B rows)
-constexpr int WARP_TY = 8;    // rows of H per block
+constexpr int WARP_TY = 8;    // thread rows per block
+constexpr int WARP_VY = 2;    // forward: output rows per thread (y and y + WARP_TY), processed as packed fp32x2
+constexpr int WARP_NZ = 4;    // forward: consecutive planes per block (software-pipelined phi loads)
 
 struct WarpDims {
     int C, D, H, W;
@@ -22,7 +24,8 @@ struct WarpDims {
     // Output slab (multi-GPU z-slab sharding): phi / out / grad_out / grad_phi hold planes [z_off, z_off+Do) of
     // axis 0 only, i.e. they are (B,*,Do,H,W) tensors; the image (and grad_img) is always the full (B,C,D,H,W).
     int Do, z_off, nvox_o;
-    unsigned z_magic;    // ceil(2^32 / Do): b = (blockIdx.z * z_magic) >> 32 for blockIdx.z < 65536
+    int zblocks;         // blocks along z per batch item: Do for the 1-plane kernels, ceil(Do / WARP_NZ) for the forward
+    unsigned z_magic;    // ceil(2^32 / zblocks): b = (blockIdx.z * z_magic) >> 32 for blockIdx.z < 65536
     float hx, hy, hz;    // (W-1)/2, (H-1)/2, (D-1)/2
     float mx, my, mz;    // W-1, H-1, D-1
     double sp0, sp1, sp2;  // 1/(D-1), 1/(H-1), 1/(W-1) as float64 (identity map, net_utils.py:81)
@@ -34,7 +37,6 @@ __device__ __forceinline__ float source_index(float g, float half_sm1, float sm1
     // ((g+1)/2)*(S-1) == RN(RN(g+1) * ((S-1)/2)): /2 is exact and (S-1)/2 is representable.
     float i = mul_rn(add_rn(g, 1.0f), half_sm1);
     if (PAD == LR_PAD_BORDER) i = fminf(sm1, fmaxf(i, 0.0f));
-    else i = clamp_index(i, sm1 + 2.0f);   // no tap is in bounds outside (-1, S): values there never matter
     return i;
 }
 
@@ -44,47 +46,28 @@ __device__ __forceinline__ float identity_coord(int idx, double spacing) {
     return sub_rn(mul_rn(v, 2.0f), 1.0f);
 }
 
-// Per-block identity-map table: the int->double conversions and fp64 multiplies are done by 41 threads once
+// Per-block identity-map table: the int->double conversions and fp64 multiplies are done by a few threads once
 // instead of by every voxel (they run on the slow XU / fp64 pipes).
+template <int ROWS>
 struct IdentTable {
-    float x[WARP_TX], y[WARP_TY], z;
+    float x[WARP_TX], y[ROWS], z;
 };
-__device__ __forceinline__ void build_ident_table(IdentTable &t, const WarpDims &g, int x0, int y0, int z) {
+template <int ROWS>
+__device__ __forceinline__ void build_ident_table(IdentTable<ROWS> &t, const WarpDims &g, int x0, int y0, int z) {
     const int tid = threadIdx.y * WARP_TX + threadIdx.x;
     if (tid < WARP_TX) t.x[tid] = identity_coord(x0 + tid, g.sp2);
-    else if (tid < WARP_TX + WARP_TY) t.y[tid - WARP_TX] = identity_coord(y0 + tid - WARP_TX, g.sp1);
-    else if (tid == WARP_TX + WARP_TY) t.z = identity_coord(z, g.sp0);
+    else if (tid < WARP_TX + ROWS) t.y[tid - WARP_TX] = identity_coord(y0 + tid - WARP_TX, g.sp1);
+    else if (tid == WARP_TX + ROWS) t.z = identity_coord(z, g.sp0);
     __syncthreads();
 }
 
-template <int PAD, int MODE, bool SCALE, bool IDENT, bool C1>
-__global__ void __launch_bounds__(WARP_TX * WARP_TY)
-    warp_forward_kernel(const float *__restrict__ img, const float *__restrict__ phi, float *__restrict__ out, WarpDims g) {
-    __shared__ IdentTable ident;
-    const int x = blockIdx.x * WARP_TX + threadIdx.x;
-    const int y = blockIdx.y * WARP_TY + threadIdx.y;
-    const int b = (int)__umulhi(blockIdx.z, g.z_magic);
-    const int z = blockIdx.z - b * g.Do;                       // plane inside the output slab
-    if (IDENT) build_ident_table(ident, g, blockIdx.x * WARP_TX, blockIdx.y * WARP_TY, z + g.z_off);
-    if (x >= g.W || y >= g.H) return;
-    const int vox = z * g.HW + y * g.W + x;
-
-    // channel c of phi addresses volume axis c; grid_sample's x is the last axis (net_utils.py:27-30)
-    const float *phi_b = phi + (int64_t)b * 3 * g.nvox_o + vox;
-    float gz = ld_stream(phi_b), gy = ld_stream(phi_b + g.nvox_o), gx = ld_stream(phi_b + 2 * (int64_t)g.nvox_o);
-    if (IDENT) {  // LiftRegDeformSubspaceBackproj.py:68  deform_field = disp_field + id_transform
-        gz = add_rn(gz, ident.z);
-        gy = add_rn(gy, ident.y[threadIdx.y]);
-        gx = add_rn(gx, ident.x[threadIdx.x]);
+// One output voxel, any padding / mode, boundary-safe: the general path.
+template <int PAD, int MODE, bool SCALE>
+__device__ __forceinline__ void warp_one(const float *__restrict__ src, float *__restrict__ dst, const WarpDims &g,
+                                         int nchan, float ix, float iy, float iz) {
+    if (PAD == LR_PAD_ZEROS) {   // no tap is in bounds outside (-1, S): values there never matter; keeps |x| < 2^22
+        ix = clamp_index(ix, g.mx + 2.0f); iy = clamp_index(iy, g.my + 2.0f); iz = clamp_index(iz, g.mz + 2.0f);
     }
-    const float ix = source_index<PAD>(gx, g.hx, g.mx);
-    const float iy = source_index<PAD>(gy, g.hy, g.my);
-    const float iz = source_index<PAD>(gz, g.hz, g.mz);
-
-    const int nchan = C1 ? 1 : g.C;   // C == 1 (the moving CT, label maps) gets a loop-free instantiation
-    const float *src = img + (int64_t)b * nchan * g.nvox;
-    float *dst = out + (int64_t)b * nchan * g.nvox_o + vox;
-
     if (MODE == LR_MODE_NEAREST) {
         const int xn = rint_i(ix), yn = rint_i(iy), zn = rint_i(iz);  // nearbyint: half to even
         const bool ok = (unsigned)xn < (unsigned)g.W && (unsigned)yn < (unsigned)g.H && (unsigned)zn < (unsigned)g.D;
@@ -100,7 +83,6 @@ __global__ void __launch_bounds__(WARP_TX * WARP_TY)
         }
         return;
     }
-
     float fx, fy, fz;
     int x0, y0, z0;
     floor_fi(ix, fx, x0);
@@ -113,30 +95,7 @@ __global__ void __launch_bounds__(WARP_TX * WARP_TY)
     const float wt[8] = {mul_rn(a00, wz0), mul_rn(a10, wz0), mul_rn(a01, wz0), mul_rn(a11, wz0),
                          mul_rn(a00, wz1), mul_rn(a10, wz1), mul_rn(a01, wz1), mul_rn(a11, wz1)};
     const int base = z0 * g.HW + y0 * g.W + x0;
-    // all eight taps inside the volume <=> 0 <= x0 <= W-2 etc.: the common case, no per-tap predicates
-    const bool interior = (unsigned)x0 < (unsigned)(g.W - 1) && (unsigned)y0 < (unsigned)(g.H - 1) &&
-                          (unsigned)z0 < (unsigned)(g.D - 1);
-    if (interior) {
-#pragma unroll 1
-        for (int c = 0; c < nchan; ++c) {
-            const float *s = src + (int64_t)c * g.nvox + base;
-            float v[8];
-            v[0] = __ldg(s); v[1] = __ldg(s + 1); v[2] = __ldg(s + g.W); v[3] = __ldg(s + g.W + 1);
-            const float *s1 = s + g.HW;
-            v[4] = __ldg(s1); v[5] = __ldg(s1 + 1); v[6] = __ldg(s1 + g.W); v[7] = __ldg(s1 + g.W + 1);
-            float acc = 0.0f;
-#pragma unroll
-            for (int t = 0; t < 8; ++t) {   // ATen: out += val * w, separately rounded, in tap order
-                float val = v[t];
-                if (SCALE) val = mul_rn(add_rn(val, 1.0f), 0.5f);   // net_utils.py:50 (img+1)/2, fused per tap
-                acc = add_rn(acc, mul_rn(val, wt[t]));
-            }
-            if (SCALE) acc = sub_rn(mul_rn(acc, 2.0f), 1.0f);       // net_utils.py:52
-            st_stream(dst + (int64_t)c * g.nvox_o, acc);
-        }
-        return;
-    }
-    // boundary voxels: per-tap bounds test, out-of-bounds taps are skipped (zeros padding)
+    // per-tap bounds test, out-of-bounds taps are skipped (ATen zeros padding; border mode never reads outside)
     const bool vx0 = (unsigned)x0 < (unsigned)g.W, vx1 = (unsigned)(x0 + 1) < (unsigned)g.W;
     const bool vy0 = (unsigned)y0 < (unsigned)g.H, vy1 = (unsigned)(y0 + 1) < (unsigned)g.H;
     const bool vz0 = (unsigned)z0 < (unsigned)g.D, vz1 = (unsigned)(z0 + 1) < (unsigned)g.D;
@@ -149,14 +108,154 @@ __global__ void __launch_bounds__(WARP_TX * WARP_TY)
         float acc = 0.0f;
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
-            if (ok[t]) {
+            if (ok[t]) {   // ATen: out += val * w, separately rounded, in tap order
                 float val = __ldg(s + off[t]);
-                if (SCALE) val = mul_rn(add_rn(val, 1.0f), 0.5f);
+                if (SCALE) val = mul_rn(add_rn(val, 1.0f), 0.5f);   // net_utils.py:50 (img+1)/2, fused per tap
                 acc = add_rn(acc, mul_rn(val, wt[t]));
             }
         }
-        if (SCALE) acc = sub_rn(mul_rn(acc, 2.0f), 1.0f);
+        if (SCALE) acc = sub_rn(mul_rn(acc, 2.0f), 1.0f);           // net_utils.py:52
         st_stream(dst + (int64_t)c * g.nvox_o, acc);
+    }
+}
+
+// Two output voxels a = (x, ya, z) and b = (x, yb, z) of one thread.  When all 16 taps are inside the volume (the
+// common case) both trilinear evaluations run as ONE packed fp32x2 instruction stream; otherwise each voxel takes
+// the scalar boundary-safe path.  gx/gy/gz hold the (already identity-corrected) map values of (a, b).
+template <int PAD, int MODE, bool SCALE>
+__device__ __forceinline__ void warp_pair(const float *__restrict__ src, float *__restrict__ dst, const WarpDims &g,
+                                          int nchan, f32x2 gx, f32x2 gy, f32x2 gz, int voxa, int voxb, bool has_b) {
+    // ATen unnormalise ((g+1)/2)*(S-1) == RN(RN(g+1) * ((S-1)/2)): /2 is exact and (S-1)/2 is representable
+    const f32x2 one = splat2(1.0f);
+    f32x2 ix = mul2(add2(gx, one), splat2(g.hx)), iy = mul2(add2(gy, one), splat2(g.hy)), iz = mul2(add2(gz, one), splat2(g.hz));
+    float ixa, ixb, iya, iyb, iza, izb;
+    unpack2(ix, ixa, ixb); unpack2(iy, iya, iyb); unpack2(iz, iza, izb);
+    if (PAD == LR_PAD_BORDER) {   // clip_coordinates
+        ixa = fminf(g.mx, fmaxf(ixa, 0.0f)); ixb = fminf(g.mx, fmaxf(ixb, 0.0f));
+        iya = fminf(g.my, fmaxf(iya, 0.0f)); iyb = fminf(g.my, fmaxf(iyb, 0.0f));
+        iza = fminf(g.mz, fmaxf(iza, 0.0f)); izb = fminf(g.mz, fmaxf(izb, 0.0f));
+        ix = pack2(ixa, ixb); iy = pack2(iya, iyb); iz = pack2(iza, izb);
+    }
+    if (MODE == LR_MODE_LINEAR) {
+        // Packed path: both y/z tap pairs inside (0 <= i < S-1) and at least one x tap inside (-1 < ix < W); NaN
+        // fails the test and takes the safe path.  The x axis is the one that diverges inside a warp (lanes run
+        // along x, so only the lanes next to a face leave the volume): its two taps are predicated instead.  A
+        // masked tap loads 0, and 0 * w added to the running sum changes nothing -- exactly ATen's "skip".
+        const float wlim = g.mx + 1.0f;
+        const bool ina = ixa > -1.0f && ixa < wlim && iya >= 0.0f && iya < g.my && iza >= 0.0f && iza < g.mz;
+        const bool inb = ixb > -1.0f && ixb < wlim && iyb >= 0.0f && iyb < g.my && izb >= 0.0f && izb < g.mz;
+        if (ina && inb) {
+            f32x2 fx, fy, fz;
+            int x0a, x0b, y0a, y0b, z0a, z0b;
+            floor2_fi(ix, fx, x0a, x0b);
+            floor2_fi(iy, fy, y0a, y0b);
+            floor2_fi(iz, fz, z0a, z0b);
+            const f32x2 wx1 = sub2(ix, fx), wx0 = sub2(add2(fx, one), ix);
+            const f32x2 wy1 = sub2(iy, fy), wy0 = sub2(add2(fy, one), iy);
+            const f32x2 wz1 = sub2(iz, fz), wz0 = sub2(add2(fz, one), iz);
+            const f32x2 a00 = mul2(wx0, wy0), a10 = mul2(wx1, wy0), a01 = mul2(wx0, wy1), a11 = mul2(wx1, wy1);
+            const f32x2 wt[8] = {mul2(a00, wz0), mul2(a10, wz0), mul2(a01, wz0), mul2(a11, wz0),
+                                 mul2(a00, wz1), mul2(a10, wz1), mul2(a01, wz1), mul2(a11, wz1)};
+            const bool la = x0a >= 0, ha = x0a < g.W - 1, lb = x0b >= 0, hb = x0b < g.W - 1;   // x taps inside?
+            // signed 32-bit element offsets (x0 may be -1): each row pointer is one IMAD.WIDE off an opaque base
+            const int a0 = z0a * g.HW + y0a * g.W + x0a, b0 = z0b * g.HW + y0b * g.W + x0b;
+            const int a1 = a0 + g.W, a2 = a0 + g.HW, a3 = a2 + g.W;
+            const int b1 = b0 + g.W, b2 = b0 + g.HW, b3 = b2 + g.W;
+            const f32x2 half = splat2(0.5f), two = splat2(2.0f);
+#pragma unroll 1
+            for (int c = 0; c < nchan; ++c) {
+                const float *sc = opaque(src + (int64_t)c * g.nvox);
+                const float *pa0 = sc + a0, *pa1 = sc + a1, *pa2 = sc + a2, *pa3 = sc + a3;
+                const float *pb0 = sc + b0, *pb1 = sc + b1, *pb2 = sc + b2, *pb3 = sc + b3;
+                f32x2 v[8];
+// masked tap: a value whose (rescaled) intensity is exactly 0: -1 when sampling (img+1)/2, else 0
+#define LR_TAP(p, ok) ((ok) ? __ldg(p) : (SCALE ? -1.0f : 0.0f))
+                v[0] = pack2(LR_TAP(pa0, la), LR_TAP(pb0, lb)); v[1] = pack2(LR_TAP(pa0 + 1, ha), LR_TAP(pb0 + 1, hb));
+                v[2] = pack2(LR_TAP(pa1, la), LR_TAP(pb1, lb)); v[3] = pack2(LR_TAP(pa1 + 1, ha), LR_TAP(pb1 + 1, hb));
+                v[4] = pack2(LR_TAP(pa2, la), LR_TAP(pb2, lb)); v[5] = pack2(LR_TAP(pa2 + 1, ha), LR_TAP(pb2 + 1, hb));
+                v[6] = pack2(LR_TAP(pa3, la), LR_TAP(pb3, lb)); v[7] = pack2(LR_TAP(pa3 + 1, ha), LR_TAP(pb3 + 1, hb));
+#undef LR_TAP
+                // ATen: out += val * w per tap, product and sum rounded separately, in tap order.  ptxas contracts
+                // mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (a single rounding) whatever the flags, so the products
+                // are packed and the two running sums are scalar adds.
+                float ra = 0.0f, rb = 0.0f;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    f32x2 val = v[t];
+                    if (SCALE) val = mul2(add2(val, one), half);   // net_utils.py:50 (img+1)/2, fused per tap
+                    float pa, pb;
+                    unpack2(mul2(val, wt[t]), pa, pb);
+                    ra = add_rn(ra, pa);
+                    rb = add_rn(rb, pb);
+                }
+                if (SCALE) {                                       // net_utils.py:52 (x2 is exact: fusing is harmless)
+                    unpack2(sub2(mul2(pack2(ra, rb), two), one), ra, rb);
+                }
+                st_stream(dst + (int64_t)c * g.nvox_o + voxa, ra);
+                if (has_b) st_stream(dst + (int64_t)c * g.nvox_o + voxb, rb);
+            }
+            return;
+        }
+    }
+    warp_one<PAD, MODE, SCALE>(src, dst + voxa, g, nchan, ixa, iya, iza);
+    if (has_b) warp_one<PAD, MODE, SCALE>(src, dst + voxb, g, nchan, ixb, iyb, izb);
+}
+
+// Forward kernel.  Thread (tx, ty) of block (bx, by, bz) owns output voxels (x, y, z) and (x, y + WARP_TY, z) for
+// WARP_NZ consecutive planes z.  The map values of plane z+1 are fetched into registers before plane z is
+// processed, so the HBM latency of the phi stream (the only compulsory traffic besides the store) is hidden behind a
+// whole plane of arithmetic instead of being exposed once per voxel.
+template <int PAD, int MODE, bool SCALE, bool IDENT, bool C1>
+__global__ void __launch_bounds__(WARP_TX * WARP_TY)
+    warp_forward_kernel(const float *__restrict__ img, const float *__restrict__ phi, float *__restrict__ out, WarpDims g) {
+    __shared__ IdentTable<WARP_TY * WARP_VY> ident;
+    __shared__ float ident_z[WARP_NZ];
+    const int x = blockIdx.x * WARP_TX + threadIdx.x;
+    const int ya = blockIdx.y * (WARP_TY * WARP_VY) + threadIdx.y;
+    const int b = g.zblocks == 1 ? (int)blockIdx.z : (int)__umulhi(blockIdx.z, g.z_magic);   // 2^32/1 does not fit the magic
+    const int z_first = (blockIdx.z - b * g.zblocks) * WARP_NZ;     // first plane (inside the output slab) of this block
+    const int nz = min(WARP_NZ, g.Do - z_first);
+    if (IDENT) {
+        if (threadIdx.y == 0 && threadIdx.x < nz) ident_z[threadIdx.x] = identity_coord(z_first + threadIdx.x + g.z_off, g.sp0);
+        build_ident_table(ident, g, blockIdx.x * WARP_TX, blockIdx.y * (WARP_TY * WARP_VY), 0);
+    }
+    if (x >= g.W || ya >= g.H) return;
+    const bool has_b = ya + WARP_TY < g.H;                     // second voxel exists (else: computed on row ya, not stored)
+    const int yb = has_b ? ya + WARP_TY : ya;
+    int voxa = z_first * g.HW + ya * g.W + x, voxb = z_first * g.HW + yb * g.W + x;
+
+    // channel c of phi addresses volume axis c; grid_sample's x is the last axis (net_utils.py:27-30)
+    const float *p0 = opaque(phi + (int64_t)b * 3 * g.nvox_o);
+    const float *p1 = opaque(p0 + g.nvox_o);
+    const float *p2 = opaque(p1 + g.nvox_o);
+    const int nchan = C1 ? 1 : g.C;   // C == 1 (the moving CT, label maps) gets a loop-free instantiation
+    const float *src = opaque(img + (int64_t)b * nchan * g.nvox);
+    float *dst = opaque(out + (int64_t)b * nchan * g.nvox_o);
+    f32x2 idx = 0, idy = 0;
+    if (IDENT) {  // LiftRegDeformSubspaceBackproj.py:68  deform_field = disp_field + id_transform
+        idx = splat2(ident.x[threadIdx.x]);
+        idy = pack2(ident.y[threadIdx.y], ident.y[has_b ? threadIdx.y + WARP_TY : threadIdx.y]);
+    }
+
+    float cza = ld_stream(p0 + (unsigned)voxa), cya = ld_stream(p1 + (unsigned)voxa), cxa = ld_stream(p2 + (unsigned)voxa);
+    float czb = ld_stream(p0 + (unsigned)voxb), cyb = ld_stream(p1 + (unsigned)voxb), cxb = ld_stream(p2 + (unsigned)voxb);
+#pragma unroll 1
+    for (int zi = 0; zi < nz; ++zi) {
+        float nza = 0.f, nya = 0.f, nxa = 0.f, nzb = 0.f, nyb = 0.f, nxb = 0.f;
+        if (zi + 1 < nz) {   // prefetch the next plane's map values
+            const unsigned na = (unsigned)(voxa + g.HW), nb = (unsigned)(voxb + g.HW);
+            nza = ld_stream(p0 + na); nya = ld_stream(p1 + na); nxa = ld_stream(p2 + na);
+            nzb = ld_stream(p0 + nb); nyb = ld_stream(p1 + nb); nxb = ld_stream(p2 + nb);
+        }
+        f32x2 gx = pack2(cxa, cxb), gy = pack2(cya, cyb), gz = pack2(cza, czb);
+        if (IDENT) {
+            gz = add2(gz, splat2(ident_z[zi]));
+            gy = add2(gy, idy);
+            gx = add2(gx, idx);
+        }
+        warp_pair<PAD, MODE, SCALE>(src, dst, g, nchan, gx, gy, gz, voxa, voxb, has_b);
+        cza = nza; cya = nya; cxa = nxa; czb = nzb; cyb = nyb; cxb = nxb;
+        voxa += g.HW; voxb += g.HW;
     }
 }
 
@@ -167,10 +266,10 @@ template <int PAD, bool SCALE, bool IDENT>
 __global__ void __launch_bounds__(WARP_TX * WARP_TY)
     warp_backward_kernel(const float *__restrict__ gout, const float *__restrict__ img, const float *__restrict__ phi,
                          float *__restrict__ gimg, float *__restrict__ gphi, WarpDims g) {
-    __shared__ IdentTable ident;
+    __shared__ IdentTable<WARP_TY> ident;
     const int x = blockIdx.x * WARP_TX + threadIdx.x;
     const int y = blockIdx.y * WARP_TY + threadIdx.y;
-    const int b = (int)__umulhi(blockIdx.z, g.z_magic);
+    const int b = g.zblocks == 1 ? (int)blockIdx.z : (int)__umulhi(blockIdx.z, g.z_magic);   // 2^32/1 does not fit the magic
     const int z = blockIdx.z - b * g.Do;
     if (IDENT) build_ident_table(ident, g, blockIdx.x * WARP_TX, blockIdx.y * WARP_TY, z + g.z_off);
     if (x >= g.W || y >= g.H) return;
@@ -239,7 +338,7 @@ __global__ void __launch_bounds__(WARP_TX * WARP_TY)
 }
 
 __global__ void __launch_bounds__(WARP_TX * WARP_TY) identity_map_kernel(float *__restrict__ out, WarpDims g) {
-    __shared__ IdentTable ident;
+    __shared__ IdentTable<WARP_TY> ident;
     const int x = blockIdx.x * WARP_TX + threadIdx.x;
     const int y = blockIdx.y * WARP_TY + threadIdx.y;
     const int z = blockIdx.z;
@@ -266,7 +365,8 @@ static WarpDims make_dims(int C, int D, int H, int W, int z_begin = 0, int z_cou
     g.Do = z_count < 0 ? D : z_count;
     g.z_off = z_begin;
     g.nvox_o = g.Do * H * W;
-    g.z_magic = (unsigned)(((1ull << 32) + (unsigned)g.Do - 1) / (unsigned)g.Do);
+    g.zblocks = g.Do;
+    g.z_magic = (unsigned)(((1ull << 32) + (unsigned)g.zblocks - 1) / (unsigned)g.zblocks);
     g.hx = (float)(W - 1) / 2.0f; g.hy = (float)(H - 1) / 2.0f; g.hz = (float)(D - 1) / 2.0f;
     g.mx = (float)(W - 1); g.my = (float)(H - 1); g.mz = (float)(D - 1);
     g.sp0 = 1.0 / (double)(D - 1); g.sp1 = 1.0 / (double)(H - 1); g.sp2 = 1.0 / (double)(W - 1);
@@ -284,8 +384,9 @@ static int check_warp_args(int B, int C, int D, int H, int W, int padding, int m
 
 // grid.z = D * (batch items of this launch) must stay <= 65535: batches are launched in chunks
 static int batch_chunk(int D) { return 65535 / D > 0 ? 65535 / D : 1; }
-static dim3 warp_grid(int nb, int D, int H, int W) {
-    return dim3((unsigned)((W + WARP_TX - 1) / WARP_TX), (unsigned)((H + WARP_TY - 1) / WARP_TY), (unsigned)(D * nb));
+static dim3 warp_grid(int nb, int D, int H, int W, int rows_per_thread = 1) {
+    const int rows = WARP_TY * rows_per_thread;
+    return dim3((unsigned)((W + WARP_TX - 1) / WARP_TX), (unsigned)((H + rows - 1) / rows), (unsigned)(D * nb));
 }
 
 template <int PAD, int MODE>
@@ -337,12 +438,14 @@ extern "C" int lr_warp_forward_slab(const float *img, const float *phi, int B, i
     if (int e = check_warp_args(B, C, D, H, W, padding, mode)) return e;
     if (int e = check_slab(D, z_begin, z_count)) return e;
     WarpDims g = make_dims(C, D, H, W, z_begin, z_count);
+    g.zblocks = (g.Do + WARP_NZ - 1) / WARP_NZ;
+    g.z_magic = (unsigned)(((1ull << 32) + (unsigned)g.zblocks - 1) / (unsigned)g.zblocks);
     cudaStream_t st = as_stream(stream);
     const bool sc = using_scale != 0, id = disp_plus_identity != 0;
-    const int chunk = batch_chunk(g.Do);
+    const int chunk = batch_chunk(g.zblocks);
     for (int b0 = 0; b0 < B; b0 += chunk) {
         const int nb = B - b0 < chunk ? B - b0 : chunk;
-        const dim3 grid = warp_grid(nb, g.Do, H, W);
+        const dim3 grid = warp_grid(nb, g.zblocks, H, W, WARP_VY);
         const float *im = img + (int64_t)b0 * C * g.nvox, *ph = phi + (int64_t)b0 * 3 * g.nvox_o;
         float *o = out + (int64_t)b0 * C * g.nvox_o;
         if (padding == LR_PAD_ZEROS) {

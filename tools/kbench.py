@@ -1,0 +1,77 @@
+#!/usr/bin/env python
+"""Quick per-kernel timing loop for kernel development (not the contract benchmark -- that is bench.py).
+
+    python tools/kbench.py [warp] [backproject] [drr] [--iters N]
+
+Times each kernel at the cfg2 / cfg1 sizes with rotating buffers (cold L2) under a CUDA graph and prints us per launch."""
+import ctypes
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from liftreg_b200 import _native, ops, synthetic  # noqa: E402
+
+VOL, DET, P, R = (160, 160, 160), (256, 256), 4, 8
+
+
+def main():
+    which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["warp", "backproject", "drr"]
+    iters = int(sys.argv[sys.argv.index("--iters") + 1]) if "--iters" in sys.argv else 400
+    dev = torch.device("cuda:0")
+    lib = _native.lib()
+    stream = torch.cuda.Stream()
+    rs = np.random.RandomState(0)
+    nv = VOL[0] * VOL[1] * VOL[2]
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())
+    poses = synthetic.wrapper_poses(60.0, P, VOL[1])
+    poses32 = np.ascontiguousarray(poses.astype(np.float32))
+    phi = torch.from_numpy((synthetic.smooth_displacement(VOL) + synthetic.identity_map_np(VOL))[None]).to(dev)
+    moving = torch.from_numpy(rs.uniform(-1, 1, (1, 1) + VOL).astype(np.float32)).to(dev)
+    proj = torch.from_numpy(rs.uniform(-1, 1, (1, P) + DET).astype(np.float32)).to(dev)
+    mu = torch.from_numpy(rs.uniform(0, 0.3, (1,) + VOL).astype(np.float32)).to(dev)
+    sets = [dict(phi=phi.clone(), moving=moving.clone(), proj=proj.clone(), mu=mu.clone(),
+                 warped=torch.empty((1, 1) + VOL, device=dev), lifted=torch.empty((1, P) + VOL, device=dev),
+                 drr=torch.empty((1, P, 240, 240), device=dev)) for _ in range(R)]
+    sp3 = np.array([2.2, 2.2, 2.2], np.float32)
+    p64 = np.ascontiguousarray(poses, np.float64)
+
+    def k_warp(s, st):
+        _native.check(lib.lr_warp_forward(vp(s["moving"]), vp(s["phi"]), 1, 1, *VOL, 0, 0, 1, 0, vp(s["warped"]), st), "warp")
+
+    def k_backproject(s, st):
+        _native.check(lib.lr_backproject_forward(vp(s["proj"]), ops._fp(poses32), 1, P, DET[0], DET[1], *VOL, vp(s["lifted"]),
+                                                 P * nv, nv, st), "backproject")
+
+    def k_drr(s, st):
+        _native.check(lib.lr_drr_forward(vp(s["mu"]), 1, *VOL, ops._dp(p64), 1, P, 240, 240, ops._fp(sp3), 0,
+                                         ctypes.c_float(0.1), vp(s["drr"]), st), "drr")
+
+    units = {"warp": (k_warp, nv, 20 * nv), "backproject": (k_backproject, P * nv, 4 * P * nv + 4 * P * DET[0] * DET[1]),
+             "drr": (k_drr, P * 240 * 240 * VOL[1], 4 * nv + 4 * P * 240 * 240)}
+    for name in which:
+        fn, n_units, nbytes = units[name]
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(stream):
+            st = ctypes.c_void_p(stream.cuda_stream)
+            fn(sets[0], st); stream.synchronize()
+            with torch.cuda.graph(g, stream=stream):
+                for r in range(R):
+                    fn(sets[r], st)
+            for _ in range(3):
+                g.replay()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(iters // R):
+                g.replay()
+            e1.record(stream)
+        torch.cuda.synchronize()
+        us = 1e3 * e0.elapsed_time(e1) / (iters // R * R)
+        print("%-12s %8.2f us  %8.1f G units/s  %7.1f GB/s (algorithmic)" % (name, us, n_units / us * 1e-3, nbytes / us * 1e-3))
+
+
+if __name__ == "__main__":
+    main()
