@@ -1,0 +1,94 @@
+"""Make an installed reference LiftReg (`import liftreg`) use the B200 kernels without editing its sources.
+
+    import liftreg_b200.dropin as dropin
+    dropin.install()            # before or after `import liftreg...`; idempotent
+    # main.py / eval.py / tools/preprocessingDRR.py now run on the CUDA kernels
+
+What is rebound:
+  liftreg.utils.sdct_projection_utils.*   -> liftreg_b200.sdct_projection_utils.*   (every public function)
+  liftreg.utils.net_utils.Bilinear / identity_map / not_normalized_identity_map / gen_identity_map
+  liftreg.layers.layers.proj_layer
+  liftreg.models.LiftRegDeformSubspaceBackproj.model._estimate_flow  -> fused backprojection written straight into
+      the encoder's (B,1+P,D,W,H) input buffer (replaces :85-98: cached 131 MB grid, grid_sample, torch.cat)
+Names that other reference modules imported with `from ... import X` before install() are rebound in those modules
+too.  Everything else in the reference (conv encoder, losses, datasets, trainer, checkpoints) is untouched.
+"""
+import importlib
+import sys
+
+from . import layers as _layers
+from . import net_utils as _net_utils
+from . import ops as _ops
+from . import sdct_projection_utils as _sdct
+
+_SDCT_NAMES = ["calc_relative_atten_coef", "calc_relative_atten_coef_cuda", "project_grid_multi", "calculate_projection",
+               "calculate_projection_wraper", "calculate_projection_wraper_with_geo_csv_file", "backproj_grids",
+               "forward_grids", "backproj_grids_with_poses", "forward_grids_with_poses", "backproject"]
+_NET_NAMES = ["Bilinear", "identity_map", "not_normalized_identity_map", "gen_identity_map"]
+
+_installed = False
+
+
+def _estimate_flow(self, moving, target_proj, poses):
+    """Drop-in for reference models/LiftRegDeformSubspaceBackproj.py:80-104.
+
+    Lines 85-98 (cached backprojection grid, F.grid_sample, .detach(), torch.cat with `moving`) become one kernel
+    that writes channels 1..P of the encoder input; channel 0 is a copy of `moving`.  Geometry comes from batch item
+    0 like the reference (:85-87).  Lines 99-104 (encoder, FC, PCA decode) are the reference's own modules."""
+    import torch
+    import torch.nn.functional as F
+    B, _, D, W, H = moving.shape
+    P = target_proj.shape[1]
+    x = torch.empty((B, 1 + P, D, W, H), device=moving.device, dtype=moving.dtype)
+    x[:, 0:1].copy_(moving)
+    with torch.no_grad():
+        _ops.backproject(target_proj.detach(), poses[0:1].detach().cpu().numpy(), (D, W, H), out=x, channel_offset=1)
+    for enc in self.encoders:
+        x = enc(x)
+    disp_field = F.linear(x, self.pca_vectors, self.pca_mean).reshape(B, 3, D, W, H)
+    return x, disp_field
+
+
+def _rebind(old_to_new):
+    """Rebind names in already-imported liftreg.* modules that still point at the replaced objects."""
+    for name, mod in list(sys.modules.items()):
+        if mod is None or not name.startswith("liftreg.") or name.startswith("liftreg_b200"):
+            continue
+        for attr, val in list(vars(mod).items()):
+            new = old_to_new.get(id(val))
+            if new is not None and val is not new:
+                setattr(mod, attr, new)
+
+
+def install(patch_model=True):
+    """Patch the reference package in place.  Returns the list of patched qualified names."""
+    global _installed
+    patched = []
+    old_to_new = {}
+
+    def swap(mod, attr, new):
+        old = getattr(mod, attr, None)
+        if old is not None and old is not new:
+            old_to_new[id(old)] = new
+        setattr(mod, attr, new)
+        patched.append("%s.%s" % (mod.__name__, attr))
+
+    ref_sdct = importlib.import_module("liftreg.utils.sdct_projection_utils")
+    for n in _SDCT_NAMES:
+        swap(ref_sdct, n, getattr(_sdct, n))
+    ref_net = importlib.import_module("liftreg.utils.net_utils")
+    for n in _NET_NAMES:
+        swap(ref_net, n, getattr(_net_utils, n))
+    ref_layers = importlib.import_module("liftreg.layers.layers")
+    swap(ref_layers, "proj_layer", _layers.proj_layer)
+    _rebind(old_to_new)
+    if patch_model:
+        try:
+            ref_model = importlib.import_module("liftreg.models.LiftRegDeformSubspaceBackproj")
+            ref_model.model._estimate_flow = _estimate_flow
+            patched.append("liftreg.models.LiftRegDeformSubspaceBackproj.model._estimate_flow")
+            _rebind(old_to_new)
+        except ImportError:      # the model needs packages (e.g. for its layers) that may be absent
+            pass
+    _installed = True
+    return patched

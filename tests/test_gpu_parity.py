@@ -441,3 +441,79 @@ def test_sharded_entry_points_world_1(dev):
     tp = cu(rs.uniform(-1, 1, (1, 3, 16, 16)).astype(np.float32), dev)
     slab, zr = sharding.backproject_sharded(tp, poses.astype(np.float32), (8, 9, 7))
     assert zr == (0, 8) and torch.equal(slab, ops.backproject(tp, poses.astype(np.float32), (8, 9, 7)))
+
+
+# ------------------------------------------------------------------ against stock PyTorch on the same GPU
+def test_against_stock_torch_cuda_ops(dev):
+    """The reference's op sequence (oracle/torch_port.py) executed by stock ATen CUDA kernels on this GPU.  ATen's
+    CUDA kernels round differently from its CPU kernels (e.g. division by a scalar becomes a multiply by the
+    reciprocal), so this is a tolerance check: <= 1e-5 relative L2 per image / volume."""
+    from liftreg_b200 import ops, synthetic
+    from oracle import torch_port
+    shape, det, P = (48, 40, 56), (72, 84), 3
+    hu = synthetic.ct_phantom(shape, seed=5, sigma=1.5, nodules=6, noise_hu=0.0)
+    mu = synthetic.hu_to_mu(hu)
+    poses = synthetic.wrapper_poses(60.0, P, shape[1])
+    ref_proj = torch_port.drr(mu, poses, det, (2.2, 2.2, 2.2), device="cuda")
+    our_proj = ops.drr_project(cu(mu[None], dev), poses, det, (2.2, 2.2, 2.2))[0].cpu().numpy()
+    assert per_image_rel_l2(our_proj, ref_proj) <= TOL
+
+    tp = cu(synthetic.normalise_projection(ref_proj)[None], dev)
+    grids = torch_port.backproj_grid(poses[None].astype(np.float32), shape, det, device="cuda").permute(0, 1, 3, 4, 5, 2)
+    ref_vol = torch_port.backproject(tp, grids)
+    our_vol = ops.backproject(tp, poses.astype(np.float32), shape)
+    for p in range(P):
+        assert rel_l2(our_vol[0, p].cpu().numpy(), ref_vol[0, p].cpu().numpy()) <= TOL
+
+    moving = cu(synthetic.hu_to_unit(hu)[None, None], dev)
+    phi = cu((synthetic.smooth_displacement(shape, max_disp=0.08) + synthetic.identity_map_np(shape))[None], dev)
+    ref_w = torch_port.warp(moving, phi, zero_boundary=True, using_scale=True)
+    our_w = ops.warp(moving, phi, zero_boundary=True, using_scale=True)
+    assert rel_l2(our_w.cpu().numpy(), ref_w.cpu().numpy()) <= TOL
+    # gradients wrt phi against autograd through stock grid_sample
+    p1 = phi.clone().requires_grad_(True); p2 = phi.clone().requires_grad_(True)
+    torch_port.warp(moving, p1, zero_boundary=True, using_scale=True).square().sum().backward()
+    ops.warp(moving, p2, zero_boundary=True, using_scale=True).square().sum().backward()
+    assert rel_l2(p2.grad.cpu().numpy(), p1.grad.cpu().numpy()) <= GRAD_TOL
+
+
+def test_model_hot_path_drop_in(dev):
+    """The two drop-in sites of LiftRegDeformSubspaceBackproj: lines 85-98 (backprojection + cat) via
+    dropin._estimate_flow's fused buffer write, and lines 68-69 (identity add + Bilinear) via the fused warp; both
+    against the reference's op sequence replayed on the CPU (oracle/torch_port.py)."""
+    import types
+    from liftreg_b200 import dropin, net_utils, ops, synthetic
+    from oracle import torch_port
+    shape, det, B, P = (20, 24, 28), (40, 36), 2, 4
+    rs = np.random.RandomState(31)
+    moving = rs.uniform(-1, 1, (B, 1) + shape).astype(np.float32)
+    target_proj = rs.uniform(-1, 1, (B, P) + det).astype(np.float32)
+    poses = np.repeat(synthetic.wrapper_poses(60.0, P, shape[1])[None], B, 0).astype(np.float32)
+    disp = np.stack([synthetic.smooth_displacement(shape, seed=s, max_disp=0.1, coarse=4) for s in (1, 2)])
+
+    # reference sequence on CPU: grids from poses[0:1], grid_sample, cat; then disp + id, Bilinear(zeros, scale)
+    grids = torch_port.backproj_grid(poses[0:1], shape, det).permute(0, 1, 3, 4, 5, 2)
+    ref_x = torch.cat([torch.from_numpy(moving), torch_port.backproject(torch.from_numpy(target_proj), grids)], dim=1)
+    ref_phi = torch.from_numpy(disp) + torch_port.identity_map(shape)
+    ref_warped = torch_port.warp(torch.from_numpy(moving), ref_phi, zero_boundary=True, using_scale=True)
+
+    # ours: a stand-in model object exposing what _estimate_flow touches (identity encoder, zero PCA basis + mean=disp)
+    captured = {}
+
+    class Capture(torch.nn.Module):
+        def forward(self, x):
+            captured["x"] = x.clone()
+            return x.reshape(x.shape[0], -1)[:, :3]
+
+    nvox = int(np.prod(shape))
+    fake = types.SimpleNamespace(encoders=[Capture()], pca_vectors=torch.zeros(3 * nvox, 3, device=dev),
+                                 pca_mean=cu(disp[0].reshape(-1), dev))
+    _, disp_field = dropin._estimate_flow(fake, cu(moving, dev), cu(target_proj, dev), torch.from_numpy(poses))
+    assert torch.equal(captured["x"].cpu(), ref_x)                      # bit-identical encoder input
+    assert disp_field.shape == (B, 3) + shape
+    id_transform = net_utils.gen_identity_map(shape, 1.0)
+    phi = cu(disp, dev) + id_transform                                   # model :68
+    warped = net_utils.Bilinear(zero_boundary=True, using_scale=True)(cu(moving, dev), phi)   # model :69
+    assert torch.equal(phi.cpu(), ref_phi) and torch.equal(warped.cpu(), ref_warped)
+    fused = ops.warp(cu(moving, dev), cu(disp, dev), zero_boundary=True, using_scale=True, disp_plus_identity=True)
+    assert torch.equal(fused.cpu(), ref_warped)
