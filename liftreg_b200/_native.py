@@ -6,7 +6,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libliftreg_b200.so")
+LIB_PATH = os.environ.get("LIFTREG_B200_LIB") or os.path.join(_HERE, "_lib", "libliftreg_b200.so")   # env: kernel experiments
 
 c_float_p = ctypes.POINTER(ctypes.c_float)
 c_double_p = ctypes.POINTER(ctypes.c_double)

@@ -20,7 +20,10 @@
 namespace lr {
 
 constexpr int BP_MAX_VIEWS = 64;   // views per launch (poses travel as kernel parameters)
-constexpr int BP_ICHUNK = 32;      // i-planes per block
+#ifndef LR_BP_ICHUNK
+#define LR_BP_ICHUNK 32
+#endif
+constexpr int BP_ICHUNK = LR_BP_ICHUNK;      // max i-planes per block (the actual chunk is balanced: ceil(d / n_chunks))
 
 struct BpPoses {
     float s[BP_MAX_VIEWS][3];
@@ -29,6 +32,7 @@ struct BpPoses {
 struct BpDims {
     int B, P, pw, ph, d, w, h;     // d = planes of axis 0 held by the output (the whole volume, or a z-slab of it)
     int i_off;                     // absolute index of the output's first plane (0 unless slab-sharded)
+    int ichunk;                    // planes per block: ceil(d / ceil(d / BP_ICHUNK)) <= BP_ICHUNK
     int p0;                        // first view of this launch
     float half_d, half_h;          // d/2, h/2 (exact)
     float pwf, phf;                // (float)pw, (float)ph
@@ -62,33 +66,34 @@ __device__ __forceinline__ float view_scale(float sy, int w, int j) {
 
 // Per-plane (u-axis) entry of the block's shared table: one LDS.128 per i instead of ~25 instructions.
 struct __align__(16) BpRow {
-    int off0;     // r0 * ph * 4: byte offset of detector row r0 inside the view
-    float n, s;   // iy - floor(iy), 1 - n
-    int mask;     // bit 0: row r0 inside the detector, bit 1: row r0+1 inside; bits 2..: min(r0 - r0 of the
-                  // previous plane, 2) (2 for the first plane of the chunk) -- drives the sliding row window
+    float n, s;   // iy - floor(iy), 1 - n   (first: an aligned register pair for the packed weight products)
+    int off0;     // r0 * ph: element offset of detector row r0 inside the view
+    int mask;     // bit 0: row r0 inside the detector, bit 1: row r0+1 inside.  Sliding row window (relative to the
+                  // previous plane of the chunk): bit 2 = moved exactly one row (reuse the upper row as the lower),
+                  // bit 3 = moved further or first plane (fetch both rows), bit 4 = upper row must be fetched
 };
 
 // Builds the table; returns (block-uniformly) whether every plane of the chunk has both rows inside the detector.
 __device__ __forceinline__ bool build_row_table(BpRow *rows, const BpDims &g, int i_begin, int i_count, float sx,
                                                 float scale) {
     int ok = 1;
-    if ((int)threadIdx.x < i_count) {
-        AxisTap t = axis_tap((float)(g.i_off + i_begin + (int)threadIdx.x) - g.half_d, sx, scale, g.pwf, g.hpw);
+    for (int t_idx = threadIdx.x; t_idx < i_count; t_idx += blockDim.x) {
+        AxisTap t = axis_tap((float)(g.i_off + i_begin + t_idx) - g.half_d, sx, scale, g.pwf, g.hpw);
         BpRow r;
-        r.off0 = t.i0 * g.ph * 4;
+        r.off0 = t.i0 * g.ph;
         r.n = t.w1;
         r.s = sub_rn(1.0f, t.w1);
         r.mask = ((unsigned)t.i0 < (unsigned)g.pw ? 1 : 0) | ((unsigned)(t.i0 + 1) < (unsigned)g.pw ? 2 : 0);
-        ok = r.mask == 3;
+        ok &= r.mask == 3;
         // consecutive planes advance the detector row by ~1..1.4 (the magnification): tell the consumer how far
         int step = 2;
-        if (threadIdx.x > 0) {
-            const AxisTap tp = axis_tap((float)(g.i_off + i_begin + (int)threadIdx.x - 1) - g.half_d, sx, scale, g.pwf, g.hpw);
+        if (t_idx > 0) {
+            const AxisTap tp = axis_tap((float)(g.i_off + i_begin + t_idx - 1) - g.half_d, sx, scale, g.pwf, g.hpw);
             const int dlt = t.i0 - tp.i0;
             step = (dlt == 0 || dlt == 1) ? dlt : 2;
         }
-        r.mask |= step << 2;
-        rows[threadIdx.x] = r;
+        r.mask |= step == 1 ? (4 | 16) : (step == 0 ? 0 : (8 | 16));
+        rows[t_idx] = r;
     }
     return __syncthreads_and(ok) != 0;
 }
@@ -104,17 +109,16 @@ __global__ void __launch_bounds__(256)
     __shared__ BpRow rows[BP_ICHUNK];
 
     const int j = blockIdx.x;
-    const int i_begin = blockIdx.y * BP_ICHUNK;
+    const int i_begin = blockIdx.y * g.ichunk;
     const int pl = blockIdx.z;           // view inside this launch
     const int p = g.p0 + pl;
     const float sx = poses.s[pl][0], sy = poses.s[pl][1], sz = poses.s[pl][2];
     const float scale = view_scale(sy, g.w, j);
-    const int i_count = min(BP_ICHUNK, g.d - i_begin);
+    const int i_count = min(g.ichunk, g.d - i_begin);
     const bool rows_ok = build_row_table(rows, g, i_begin, i_count, sx, scale);
 
     const int64_t proj_batch = (int64_t)g.P * g.proj_view_stride;
     const int64_t plane_bytes = (int64_t)g.w * g.h * 4;
-    const int row_bytes = g.ph * 4;
     for (int k = threadIdx.x; k < g.h; k += blockDim.x) {
         const AxisTap tv = axis_tap((float)k - g.half_h, sz, scale, g.phf, g.hph);
         const float wq = tv.w1, e = sub_rn(1.0f, wq);
@@ -123,7 +127,7 @@ __global__ void __launch_bounds__(256)
         // per-sample inner loop stays branch-free: LDS.128, 4 weights, 4 loads, 1 mul + 3 fma, 1 store
 #pragma unroll 1
         for (int b = 0; b < g.B; ++b) {
-            const char *pv = (const char *)(proj + b * proj_batch + (int64_t)p * g.proj_view_stride + tv.i0);
+            const float *pvf = proj + b * proj_batch + (int64_t)p * g.proj_view_stride + tv.i0;
             char *o = (char *)(out + b * g.out_batch_stride + (int64_t)p * g.out_chan_stride +
                                ((int64_t)i_begin * g.w + j) * g.h + k);
             if (rows_ok && c0 && c1) {
@@ -131,28 +135,37 @@ __global__ void __launch_bounds__(256)
                 // Sliding window over detector rows: this thread's two columns of rows r0, r0+1 stay in registers;
                 // when the next plane moves one row down only the new row is fetched (2.4 loads / sample on average
                 // instead of 4 -- the kernel is bound by L1 wavefronts, ncu: lsu data-pipe 68 %).
+                // The step (0, 1 or 2+ rows) is block-uniform; it is applied with predicated moves / loads rather
+                // than branches, which keeps the loop body straight-line (~23 SASS per sample).
+                const float *base = opaque(pvf);      // row offsets are non-negative here: one IMAD.WIDE.U32 per pointer
                 float va = 0.0f, vb = 0.0f, vc = 0.0f, vd = 0.0f;
+                const f32x2 e2 = splat2(e), w2 = splat2(wq);
 #pragma unroll 4
                 for (int ii = 0; ii < i_count; ++ii) {
                     const BpRow r = rows[ii];
-                    const int step = r.mask >> 2;             // block-uniform
-                    const float *q1 = (const float *)(pv + r.off0 + row_bytes);
-                    if (step == 1) {
-                        va = vc; vb = vd;
-                        vc = __ldg(q1); vd = __ldg(q1 + 1);
-                    } else if (step != 0) {
-                        const float *q0 = (const float *)(pv + r.off0);
-                        va = __ldg(q0); vb = __ldg(q0 + 1); vc = __ldg(q1); vd = __ldg(q1 + 1);
+                    if (r.mask & 4) { va = vc; vb = vd; }     // moved exactly one row down: reuse the upper row
+                    if (r.mask & 8) {                         // moved further (or first plane): fetch the lower row too
+                        const float *q0 = base + (unsigned)r.off0;
+                        va = __ldg(q0); vb = __ldg(q0 + 1);
                     }
-                    st_stream((float *)o, bilerp(va, vb, vc, vd, r.s, r.n, e, wq));
+                    if (r.mask & 16) {
+                        const float *q1 = base + (unsigned)(r.off0 + g.ph);
+                        vc = __ldg(q1); vd = __ldg(q1 + 1);
+                    }
+                    // weights (n,s) x e and (n,s) x w as two packed products: (sw, nw) and (se, ne)
+                    float sw, nw, se, ne;
+                    const f32x2 ns = pack2(r.n, r.s);
+                    unpack2(mul2(ns, e2), sw, nw);
+                    unpack2(mul2(ns, w2), se, ne);
+                    st_stream((float *)o, fma_rn(vd, se, fma_rn(vc, sw, fma_rn(vb, ne, mul_rn(va, nw)))));
                     o += plane_bytes;
                 }
             } else {
                 // rays leaving the detector: per-tap predicates (zeros padding)
                 for (int ii = 0; ii < i_count; ++ii) {
                     const BpRow r = rows[ii];
-                    const float *q0 = (const float *)(pv + r.off0);
-                    const float *q1 = (const float *)(pv + r.off0 + row_bytes);
+                    const float *q0 = pvf + r.off0;
+                    const float *q1 = q0 + g.ph;
                     const bool rv0 = (r.mask & 1) != 0, rv1 = (r.mask & 2) != 0;
                     const float va = (rv0 && c0) ? __ldg(q0) : 0.0f, vb = (rv0 && c1) ? __ldg(q0 + 1) : 0.0f;
                     const float vc = (rv1 && c0) ? __ldg(q1) : 0.0f, vd = (rv1 && c1) ? __ldg(q1 + 1) : 0.0f;
@@ -169,12 +182,12 @@ __global__ void __launch_bounds__(256)
     backproject_backward_kernel(const float *__restrict__ gout, float *__restrict__ gproj, BpDims g, BpPoses poses) {
     __shared__ BpRow rows[BP_ICHUNK];
     const int j = blockIdx.x;
-    const int i_begin = blockIdx.y * BP_ICHUNK;
+    const int i_begin = blockIdx.y * g.ichunk;
     const int pl = blockIdx.z;
     const int p = g.p0 + pl;
     const float sx = poses.s[pl][0], sy = poses.s[pl][1], sz = poses.s[pl][2];
     const float scale = view_scale(sy, g.w, j);
-    const int i_count = min(BP_ICHUNK, g.d - i_begin);
+    const int i_count = min(g.ichunk, g.d - i_begin);
     build_row_table(rows, g, i_begin, i_count, sx, scale);
     float *pv = gproj + (int64_t)p * g.proj_view_stride;
     const int64_t proj_batch = (int64_t)g.P * g.proj_view_stride;
@@ -188,7 +201,7 @@ __global__ void __launch_bounds__(256)
             const BpRow r = rows[ii];
             const bool rv0 = (r.mask & 1) != 0, rv1 = (r.mask & 2) != 0;
             const float nw = mul_rn(r.s, e), ne = mul_rn(r.s, wq), sw = mul_rn(r.n, e), se = mul_rn(r.n, wq);
-            float *q0 = pv + (r.off0 / 4 + tv.i0);
+            float *q0 = pv + (r.off0 + tv.i0);
             float *q1 = q0 + g.ph;
             const float *ob = o;
 #pragma unroll 1
@@ -229,9 +242,12 @@ static int fill_dims(BpDims &g, int B, int P, int pw, int ph, int d_total, int w
     const int d = i_count < 0 ? d_total : i_count;
     LR_REQUIRE(i_begin >= 0 && d > 0 && i_begin + d <= d_total, "backproject: slab [%d, %d) is not inside [0, %d)", i_begin,
                i_begin + d, d_total);
-    LR_REQUIRE(d <= 65535 * BP_ICHUNK && w < (1 << 30), "backproject: volume too large for the launch grid");
+    LR_REQUIRE(d <= 65535 * (BP_ICHUNK / 2) && w < (1 << 30), "backproject: volume too large for the launch grid");
     LR_REQUIRE((int64_t)(pw + 4) * ph < (1ll << 31) && (int64_t)w * h < (1ll << 31), "backproject: detector / plane too large for 32-bit offsets");
     g.B = B; g.P = P; g.pw = pw; g.ph = ph; g.d = d; g.w = w; g.h = h; g.p0 = 0; g.i_off = i_begin;
+    const int n_chunks = (d + BP_ICHUNK - 1) / BP_ICHUNK;
+    g.ichunk = (((d + n_chunks - 1) / n_chunks + 3) / 4) * 4;      // balanced, multiple of the unroll factor
+    if (g.ichunk > BP_ICHUNK) g.ichunk = BP_ICHUNK;
     g.half_d = (float)((double)d_total / 2.0); g.half_h = (float)((double)h / 2.0);
     g.pwf = (float)pw; g.phf = (float)ph;
     g.hpw = (float)(pw - 1) / 2.0f; g.hph = (float)(ph - 1) / 2.0f;
@@ -263,7 +279,7 @@ extern "C" int lr_backproject_forward_slab(const float *proj, const float *poses
         for (int q = 0; q < np; ++q)
             for (int c = 0; c < 3; ++c) ps.s[q][c] = poses[(p0 + q) * 3 + c];
         g.p0 = p0;
-        dim3 grid((unsigned)w, (unsigned)((d + BP_ICHUNK - 1) / BP_ICHUNK), (unsigned)np);
+        dim3 grid((unsigned)w, (unsigned)((d + g.ichunk - 1) / g.ichunk), (unsigned)np);
         backproject_forward_kernel<<<grid, block_threads(h), 0, as_stream(stream)>>>(proj, out, g, ps);
         if (int e = check_launch("backproject_forward_kernel")) return e;
     }
@@ -289,7 +305,7 @@ extern "C" int lr_backproject_backward(const float *grad_out, int64_t go_batch_s
         for (int q = 0; q < np; ++q)
             for (int c = 0; c < 3; ++c) ps.s[q][c] = poses[(p0 + q) * 3 + c];
         g.p0 = p0;
-        dim3 grid((unsigned)w, (unsigned)((d + BP_ICHUNK - 1) / BP_ICHUNK), (unsigned)np);
+        dim3 grid((unsigned)w, (unsigned)((d + g.ichunk - 1) / g.ichunk), (unsigned)np);
         backproject_backward_kernel<<<grid, block_threads(h), 0, as_stream(stream)>>>(grad_out, grad_proj, g, ps);
         if (int e = check_launch("backproject_backward_kernel")) return e;
     }

@@ -20,7 +20,7 @@ VOL, DET, P, R = (160, 160, 160), (256, 256), 4, 8
 
 def main():
     which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["warp", "backproject", "drr"]
-    iters = int(sys.argv[sys.argv.index("--iters") + 1]) if "--iters" in sys.argv else 400
+    iters = int(sys.argv[sys.argv.index("--iters") + 1]) if "--iters" in sys.argv else 2000
     dev = torch.device("cuda:0")
     lib = _native.lib()
     stream = torch.cuda.Stream()
