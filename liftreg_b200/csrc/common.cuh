@@ -89,7 +89,18 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
     return r;
 }
-// packed floor for two values already known to lie in [0, 2^22): float floors and int floors
+// a*b rounded on its own, for products that feed an add: ptxas (12.9) contracts mul.rn.f32x2 + add.rn.f32x2 into a
+// single-rounding FFMA2 whatever the flags (it does not do that to the scalar .rn forms).  `zero` must be a
+// run-time +0 that the compiler cannot see through (a kernel parameter): fma(a, b, +0) == RN(a*b).
+__device__ __forceinline__ f32x2 mul2_sep(f32x2 a, f32x2 b, f32x2 zero) { return fma2(a, b, zero); }
+// packed Markstein division by a loop-invariant (see div_const)
+__device__ __forceinline__ f32x2 div_const2(f32x2 x, ConstDiv k) {
+    const f32x2 rc = splat2(k.rc);
+    const f32x2 q0 = mul2(x, rc);
+    const f32x2 r = fma2(splat2(-k.c), q0, x);
+    return fma2(r, rc, q0);
+}
+// packed floor for two values with |x| < 2^22: float floors and int floors
 __device__ __forceinline__ void floor2_fi(f32x2 x, f32x2 &f, int &i_lo, int &i_hi) {
     const f32x2 M = splat2(12582912.0f);
     const f32x2 t = add2(x, M);

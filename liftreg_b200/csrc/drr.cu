@@ -16,7 +16,9 @@
 namespace lr {
 
 constexpr int DRR_MAX_VIEWS = 128;  // (volume, pose) pairs per launch; poses travel as kernel parameters
-constexpr int DRR_ROWS = 4;         // detector rows (u) per block: 4 warps
+constexpr int DRR_ROWS = 4;         // detector rows (u) per block in the one-ray-per-thread kernels (backward, grid)
+constexpr int DRR_PAIRS = 2;        // forward: ray pairs (2 detector rows each) per block along u
+constexpr int DRR_SEGS = 4;         // forward: every ray is cut into 4 runs of ceil(w/4) coronal planes, one warp each
 
 struct DrrView {
     float sx, sy, sz;
@@ -35,12 +37,15 @@ struct DrrDims {
     float hd, hw, hh;          // (d-1)/2, (w-1)/2, (h-1)/2 : ((g+1)/2)*(S-1) == (g+1)*((S-1)/2) exactly
     float lim_x, lim_z;        // clip half-widths d/2+2, h/2+2
     float out_scale;
+    float zero;                // +0.0f the compiler cannot constant-fold (see mul2_sep)
+    int seg_len;               // planes per ray run in the forward kernel: ceil(w / DRR_SEGS)
     int64_t nvox;
 };
 
 struct Ray {
     float sx, sy, sz, Dx, Dy, Dz, r2, dx;
     int j0, j1;  // inclusive range of coronal planes that may touch the volume
+    bool clipped;  // j0..j1 came from the clip (coordinates stay within a few voxels of the volume)
 };
 
 __device__ __forceinline__ Ray ray_setup(const DrrView &vw, const DrrDims &g, int u, int v) {
@@ -70,7 +75,8 @@ __device__ __forceinline__ Ray ray_setup(const DrrView &vw, const DrrDims &g, in
     r.j0 = max(0, (int)floorf(t0) - 1);
     r.j1 = min(g.w - 1, (int)ceilf(t1) + 1);
     if (!(t1 >= t0)) { r.j0 = 0; r.j1 = -1; }
-    if (!(r.sy > (float)(g.w - 1))) { r.j0 = 0; r.j1 = g.w - 1; }  // emitter inside the slab: no clipping
+    r.clipped = r.sy > (float)(g.w - 1);
+    if (!r.clipped) { r.j0 = 0; r.j1 = g.w - 1; }  // emitter inside the slab: no clipping
     return r;
 }
 
@@ -127,46 +133,164 @@ __device__ __forceinline__ unsigned taps_mask(const Taps &t, const DrrDims &g) {
     return (vz0 ? mxy : 0u) | ((vz1 ? mxy : 0u) << 4);
 }
 
-__global__ void __launch_bounds__(32 * DRR_ROWS)
-    drr_forward_kernel(const float *__restrict__ vol, float *__restrict__ proj, DrrDims g, DrrViews views) {
-    const int v = blockIdx.x * 32 + threadIdx.x;
-    const int u = blockIdx.y * DRR_ROWS + threadIdx.y;
-    if (v >= g.rh || u >= g.rd) return;
-    const DrrView vw = views.v[blockIdx.z];
-    const Ray r = ray_setup(vw, g, u, v);
-    const float *V = vol + (int64_t)vw.vol * g.nvox;
+// One ray, scalar, boundary-safe: the general path (also used by rays whose pair partner is missing).
+__device__ __forceinline__ float march_ray(const float *__restrict__ V, const Ray &r, const DrrDims &g, int jlo, int jhi) {
     const int sy = g.h, sz = g.w * g.h;
-
     float acc = 0.0f;
-    float jf = (float)r.j0;
-    for (int j = r.j0; j <= r.j1; ++j, jf += 1.0f) {
+    const int ja = max(r.j0, jlo), jb = min(r.j1, jhi);
+    float jf = (float)ja;
+    for (int j = ja; j <= jb; ++j, jf += 1.0f) {
         const Sample s = ray_point(r, g, jf);
         const Taps t = make_taps(s, g);
+        const unsigned m = taps_mask(t, g);
+        if (m == 0u) continue;                                  // contributes exactly +0
         const float *b = V + t.base;
         float o = 0.0f;
-        if (taps_interior(t, g)) {
-            const float *b1 = b + sy, *b2 = b + sz, *b3 = b2 + sy;
-            const float v0 = __ldg(b), v1 = __ldg(b + 1), v2 = __ldg(b1), v3 = __ldg(b1 + 1);
-            const float v4 = __ldg(b2), v5 = __ldg(b2 + 1), v6 = __ldg(b3), v7 = __ldg(b3 + 1);
-            // ATen: out += val*w per tap, separately rounded, in tap order
-            o = add_rn(o, mul_rn(v0, t.wt[0])); o = add_rn(o, mul_rn(v1, t.wt[1]));
-            o = add_rn(o, mul_rn(v2, t.wt[2])); o = add_rn(o, mul_rn(v3, t.wt[3]));
-            o = add_rn(o, mul_rn(v4, t.wt[4])); o = add_rn(o, mul_rn(v5, t.wt[5]));
-            o = add_rn(o, mul_rn(v6, t.wt[6])); o = add_rn(o, mul_rn(v7, t.wt[7]));
-        } else {
-            const unsigned m = taps_mask(t, g);
-            if (m == 0u) continue;                                  // contributes exactly +0
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const int off = (c & 1) + ((c >> 1) & 1) * sy + (c >> 2) * sz;
-                if ((m >> c) & 1u) o = add_rn(o, mul_rn(__ldg(b + off), t.wt[c]));
+        for (int c = 0; c < 8; ++c) {                           // ATen: out += val*w per tap, separately rounded
+            const int off = (c & 1) + ((c >> 1) & 1) * sy + (c >> 2) * sz;
+            if ((m >> c) & 1u) o = add_rn(o, mul_rn(__ldg(b + off), t.wt[c]));
+        }
+        acc = add_rn(acc, o);                                   // sum over the ray (sdct:81), j ascending
+    }
+    return acc;
+}
+
+__device__ __forceinline__ float finish_ray(float acc, const Ray &r, const DrrDims &g) {
+    float o = mul_rn(acc, r.dx);                                // * dx (sdct:81)
+    if (g.out_scale != 1.0f) o = mul_rn(o, g.out_scale);        // *= 0.1 (sdct:85)
+    return o;
+}
+
+// Forward kernel.  A thread owns the two rays (u, v) and (u+1, v): neighbours on detector axis 0, which have almost
+// the same clip range and whose taps overlap in L1.  Both fp32 chains run as ONE packed fp32x2 stream while all 16
+// taps are inside the volume; entry / exit samples take the scalar masked path.
+// Ray-segment accumulation: a detector image has too few rays to fill 148 SMs (cfg 1: 3.8 k pair-warps for 9.5 k
+// warp slots, ncu: 26 % warps active), so every ray is cut into DRR_SEGS runs of seg_len = ceil(w / DRR_SEGS) planes
+// marched by different warps; the run sums are combined in run order.  The summation order is therefore
+//     sum_{s} ( sum_{j in run s} sample_j ),  both levels ascending, fp32
+// which the oracle reproduces (seg_len argument); the reference's own order is torch.sum's vectorised cascade.
+__global__ void __launch_bounds__(32 * DRR_PAIRS * DRR_SEGS)
+    drr_forward_kernel(const float *__restrict__ vol, float *__restrict__ proj, DrrDims g, DrrViews views) {
+    __shared__ float2 part[DRR_SEGS][DRR_PAIRS][32];
+    const int v = blockIdx.x * 32 + threadIdx.x;
+    const int ua = (blockIdx.y * DRR_PAIRS + threadIdx.y) * 2;
+    const int seg = threadIdx.z;
+    const bool live = v < g.rh && ua < g.rd;
+    const bool has_b = ua + 1 < g.rd;
+    float acca = 0.0f, accb = 0.0f;
+    Ray ra, rb;
+    if (live) {
+    const DrrView vw = views.v[blockIdx.z];
+    ra = ray_setup(vw, g, ua, v);
+    rb = ray_setup(vw, g, has_b ? ua + 1 : ua, v);
+    const float *V = opaque(vol + (int64_t)vw.vol * g.nvox);
+    const int seg_lo = seg * g.seg_len, seg_hi = min(g.w, seg_lo + g.seg_len) - 1;   // this warp's run of planes
+
+    if (!(ra.clipped && rb.clipped)) {          // unusual geometry (emitter inside the slab): scalar path only
+        acca = march_ray(V, ra, g, seg_lo, seg_hi);
+        accb = march_ray(V, rb, g, seg_lo, seg_hi);
+    } else {
+    const f32x2 zero = splat2(g.zero), one = splat2(1.0f), mone = splat2(-1.0f);
+    const f32x2 Dx = pack2(ra.Dx, rb.Dx), Dy = pack2(ra.Dy, rb.Dy), Dz = pack2(ra.Dz, rb.Dz), r2 = pack2(ra.r2, rb.r2);
+    const f32x2 sx = splat2(ra.sx), sy2 = splat2(ra.sy), sz2 = splat2(ra.sz);
+    const unsigned sy = (unsigned)g.h, sz = (unsigned)(g.w * g.h);
+    // union of the two clip ranges; outside its own range a ray has no tap in bounds and contributes exactly +0
+    const int ea = ra.j1 < ra.j0, eb = rb.j1 < rb.j0;
+    int j0 = ea ? rb.j0 : (eb ? ra.j0 : min(ra.j0, rb.j0));
+    int j1 = ea ? rb.j1 : (eb ? ra.j1 : max(ra.j1, rb.j1));
+    j0 = max(j0, seg_lo); j1 = min(j1, seg_hi);
+
+    float jf = (float)j0;
+    for (int j = j0; j <= j1; ++j, jf += 1.0f) {
+        // sdct:50-56 + flip (:76) + ATen unnormalise, both rays at once
+        const f32x2 T = mul2(r2, splat2(sub_rn(jf, ra.sy)));
+        const f32x2 X = add2(mul2_sep(Dx, T, zero), sx), Y = add2(mul2_sep(Dy, T, zero), sy2), Z = add2(mul2_sep(Dz, T, zero), sz2);
+        const f32x2 g0 = div_const2(X, g.div_x);                    // X/d*2
+        const f32x2 g1 = add2(div_const2(Y, g.div_y), mone);        // Y/(w-1)*2 + -1
+        const f32x2 g2 = div_const2(Z, g.div_z);                    // Z/h*2
+        const f32x2 iz = mul2(add2(g0, one), splat2(g.hd));
+        const f32x2 iy = mul2(add2(g1, one), splat2(g.hw));
+        const f32x2 ix = mul2(add2(g2, one), splat2(g.hh));
+        f32x2 fx, fy, fz;
+        int x0a, x0b, y0a, y0b, z0a, z0b;
+        floor2_fi(ix, fx, x0a, x0b);       // clipped rays stay within a few voxels of the volume: |x| << 2^22
+        floor2_fi(iy, fy, y0a, y0b);
+        floor2_fi(iz, fz, z0a, z0b);
+        const f32x2 wx1 = sub2(ix, fx), wx0 = sub2(add2(fx, one), ix);
+        const f32x2 wy1 = sub2(iy, fy), wy0 = sub2(add2(fy, one), iy);
+        const f32x2 wz1 = sub2(iz, fz), wz0 = sub2(add2(fz, one), iz);
+        const f32x2 a00 = mul2(wx0, wy0), a10 = mul2(wx1, wy0), a01 = mul2(wx0, wy1), a11 = mul2(wx1, wy1);
+        const f32x2 wt[8] = {mul2(a00, wz0), mul2(a10, wz0), mul2(a01, wz0), mul2(a11, wz0),
+                             mul2(a00, wz1), mul2(a10, wz1), mul2(a01, wz1), mul2(a11, wz1)};
+        const bool ina = (unsigned)x0a < (unsigned)(g.h - 1) && (unsigned)y0a < (unsigned)(g.w - 1) && (unsigned)z0a < (unsigned)(g.d - 1);
+        const bool inb = (unsigned)x0b < (unsigned)(g.h - 1) && (unsigned)y0b < (unsigned)(g.w - 1) && (unsigned)z0b < (unsigned)(g.d - 1);
+        const int basea = (z0a * g.w + y0a) * g.h + x0a, baseb = (z0b * g.w + y0b) * g.h + x0b;
+        if (ina && inb) {
+            const unsigned a0 = (unsigned)basea, b0 = (unsigned)baseb;
+            const float *pa0 = V + a0, *pa1 = V + (a0 + sy), *pa2 = V + (a0 + sz), *pa3 = V + (a0 + sz + sy);
+            const float *pb0 = V + b0, *pb1 = V + (b0 + sy), *pb2 = V + (b0 + sz), *pb3 = V + (b0 + sz + sy);
+            f32x2 val[8];
+            val[0] = pack2(__ldg(pa0), __ldg(pb0)); val[1] = pack2(__ldg(pa0 + 1), __ldg(pb0 + 1));
+            val[2] = pack2(__ldg(pa1), __ldg(pb1)); val[3] = pack2(__ldg(pa1 + 1), __ldg(pb1 + 1));
+            val[4] = pack2(__ldg(pa2), __ldg(pb2)); val[5] = pack2(__ldg(pa2 + 1), __ldg(pb2 + 1));
+            val[6] = pack2(__ldg(pa3), __ldg(pb3)); val[7] = pack2(__ldg(pa3 + 1), __ldg(pb3 + 1));
+            f32x2 o = splat2(0.0f);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) o = add2(o, mul2_sep(val[c], wt[c], zero));   // ATen: out += val*w, no fma
+            float oa, ob;
+            unpack2(o, oa, ob);
+            acca = add_rn(acca, oa);                                                   // sum over the ray (sdct:81)
+            accb = add_rn(accb, ob);
+        } else {
+            float w_a[8], w_b[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) unpack2(wt[c], w_a[c], w_b[c]);
+            const unsigned vxa0 = (unsigned)x0a < (unsigned)g.h, vxa1 = (unsigned)(x0a + 1) < (unsigned)g.h;
+            const unsigned vya0 = (unsigned)y0a < (unsigned)g.w, vya1 = (unsigned)(y0a + 1) < (unsigned)g.w;
+            const unsigned vza0 = (unsigned)z0a < (unsigned)g.d, vza1 = (unsigned)(z0a + 1) < (unsigned)g.d;
+            const unsigned vxb0 = (unsigned)x0b < (unsigned)g.h, vxb1 = (unsigned)(x0b + 1) < (unsigned)g.h;
+            const unsigned vyb0 = (unsigned)y0b < (unsigned)g.w, vyb1 = (unsigned)(y0b + 1) < (unsigned)g.w;
+            const unsigned vzb0 = (unsigned)z0b < (unsigned)g.d, vzb1 = (unsigned)(z0b + 1) < (unsigned)g.d;
+            const unsigned mxa = vxa0 | (vxa1 << 1), mxya = (vya0 ? mxa : 0u) | ((vya1 ? mxa : 0u) << 2);
+            const unsigned mxb = vxb0 | (vxb1 << 1), mxyb = (vyb0 ? mxb : 0u) | ((vyb1 ? mxb : 0u) << 2);
+            const unsigned ma = (vza0 ? mxya : 0u) | ((vza1 ? mxya : 0u) << 4);
+            const unsigned mb = (vzb0 ? mxyb : 0u) | ((vzb1 ? mxyb : 0u) << 4);
+            if (ma != 0u) {
+                float o = 0.0f;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int off = (c & 1) + ((c >> 1) & 1) * (int)sy + (c >> 2) * (int)sz;
+                    if ((ma >> c) & 1u) o = add_rn(o, mul_rn(__ldg(V + (basea + off)), w_a[c]));
+                }
+                acca = add_rn(acca, o);
+            }
+            if (mb != 0u) {
+                float o = 0.0f;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int off = (c & 1) + ((c >> 1) & 1) * (int)sy + (c >> 2) * (int)sz;
+                    if ((mb >> c) & 1u) o = add_rn(o, mul_rn(__ldg(V + (baseb + off)), w_b[c]));
+                }
+                accb = add_rn(accb, o);
             }
         }
-        acc = add_rn(acc, o);                                       // sum over the ray (sdct:81), j ascending
     }
-    float o = mul_rn(acc, r.dx);                                    // * dx (sdct:81)
-    if (g.out_scale != 1.0f) o = mul_rn(o, g.out_scale);            // *= 0.1 (sdct:85)
-    proj[((int64_t)(g.view0 + blockIdx.z) * g.rd + u) * g.rh + v] = o;
+    }   // packed / scalar
+    }   // live
+    part[seg][threadIdx.y][threadIdx.x] = make_float2(acca, accb);
+    __syncthreads();
+    if (seg == 0 && live) {
+        float ta = part[0][threadIdx.y][threadIdx.x].x, tb = part[0][threadIdx.y][threadIdx.x].y;
+#pragma unroll
+        for (int s2 = 1; s2 < DRR_SEGS; ++s2) {       // run sums combined in run order
+            ta = add_rn(ta, part[s2][threadIdx.y][threadIdx.x].x);
+            tb = add_rn(tb, part[s2][threadIdx.y][threadIdx.x].y);
+        }
+        float *out = proj + ((int64_t)(g.view0 + blockIdx.z) * g.rd + ua) * g.rh + v;
+        out[0] = finish_ray(ta, ra, g);
+        if (has_b) out[g.rh] = finish_ray(tb, rb, g);
+    }
 }
 
 // Adjoint wrt the volume: every sample scatters (go*out_scale*dx) * w_tap into its 8 taps (RED.ADD.F32).
@@ -239,6 +363,8 @@ static int fill_dims(DrrDims &g, int B, int d, int w, int h, int n_pose_sets, in
     g.lim_x = d > 1 ? (float)d / 2.0f + 2.0f + (float)d / (float)(d - 1) : 3.0e38f;
     g.lim_z = h > 1 ? (float)h / 2.0f + 2.0f + (float)h / (float)(h - 1) : 3.0e38f;
     g.out_scale = out_scale;
+    g.zero = 0.0f;
+    g.seg_len = (w + DRR_SEGS - 1) / DRR_SEGS;
     g.nvox = (int64_t)d * w * h;
     return LR_OK;
 }
@@ -273,8 +399,8 @@ extern "C" int lr_drr_forward(const float *vol, int B, int d, int w, int h, cons
     if (int e = fill_dims(g, B, d, w, h, n_pose_sets, P, rd, rh, spacing, y_norm_mode, out_scale)) return e;
     return for_each_view_chunk(poses, n_pose_sets, B, P, [&](int n, const DrrViews &vs, int v0) {
         g.view0 = v0;
-        dim3 grid((unsigned)((rh + 31) / 32), (unsigned)((rd + DRR_ROWS - 1) / DRR_ROWS), (unsigned)n);
-        drr_forward_kernel<<<grid, dim3(32, DRR_ROWS), 0, as_stream(stream)>>>(vol, proj, g, vs);
+        dim3 grid((unsigned)((rh + 31) / 32), (unsigned)((rd + 2 * DRR_PAIRS - 1) / (2 * DRR_PAIRS)), (unsigned)n);
+        drr_forward_kernel<<<grid, dim3(32, DRR_PAIRS, DRR_SEGS), 0, as_stream(stream)>>>(vol, proj, g, vs);
         return check_launch("drr_forward_kernel");
     });
 }

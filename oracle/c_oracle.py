@@ -75,8 +75,16 @@ def project_grid(poses, resolution, obj_shape, spacing, y_mode=0, want_grid=True
     return grid, dx
 
 
-def drr_forward(vol, poses, resolution, spacing, y_mode=0, out_scale=0.1, acc64=False, want_samples=False):
-    """sdct:59-86.  vol (d,w,h) or (B,d,w,h) -> proj (P,rd,rh) or (B,P,rd,rh)."""
+DRR_SEGS = 4    # liftreg_b200/csrc/drr.cu DRR_SEGS: the kernel sums each ray in 4 runs of ceil(w/4) planes
+
+
+def kernel_seg_len(w):
+    return (int(w) + DRR_SEGS - 1) // DRR_SEGS
+
+
+def drr_forward(vol, poses, resolution, spacing, y_mode=0, out_scale=0.1, acc64=False, want_samples=False, seg_len=0):
+    """sdct:59-86.  vol (d,w,h) or (B,d,w,h) -> proj (P,rd,rh) or (B,P,rd,rh).
+    seg_len=0: plain sequential ray sum; seg_len=kernel_seg_len(w): the CUDA kernel's ray-segment order."""
     vol = _f32(vol); squeeze = vol.ndim == 3
     if squeeze:
         vol = vol[None]
@@ -87,7 +95,7 @@ def drr_forward(vol, poses, resolution, spacing, y_mode=0, out_scale=0.1, acc64=
     proj = np.empty((B, P, rd, rh), np.float32)
     samples = np.empty((P, rd, rh, w), np.float32) if want_samples else None
     lib().lro_drr_forward(_p(vol), B, d, w, h, poses.ctypes.data_as(_f64p), P, rd, rh, _p(sp), y_mode,
-                          ctypes.c_float(out_scale), int(acc64), _p(proj), _p(samples))
+                          ctypes.c_float(out_scale), int(acc64), int(seg_len), _p(proj), _p(samples))
     proj = proj[0] if squeeze else proj
     return (proj, samples) if want_samples else proj
 

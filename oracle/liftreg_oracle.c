@@ -41,7 +41,9 @@
  * fmaf() calls below (torch's CPU norm and 2-D sampler do contract).
  * The one order this file does NOT reproduce is torch.sum's vectorised
  * cascade over the ray (sdct:81); rays are summed sequentially in fp32
- * (acc64=0) or in double (acc64=1).  That is a <=2e-7 relative effect.
+ * (acc64=0) or in double (acc64=1), optionally in runs of seg_len planes
+ * whose sums are then added in order (the CUDA kernel's ray-segment
+ * order).  All of these differ by <=2e-7 relative.
  */
 #include <math.h>
 #include <stdint.h>
@@ -181,10 +183,11 @@ LRO_API void lro_project_grid(const double *poses, int P, int rd, int rh, int d,
 }
 
 /* vol (B,d,w,h); proj (B,P,rd,rh); samples (optional, B==1 only): (P,rd,rh,w) pre-sum values.
- * proj = ((sum_j sample) * dx) * out_scale   -- sdct:81,85 */
+ * proj = ((sum_j sample) * dx) * out_scale   -- sdct:81,85
+ * seg_len > 0: the ray is summed in runs of seg_len planes, run sums added in run order (fp32). */
 LRO_API void lro_drr_forward(const float *vol, int B, int d, int w, int h, const double *poses, int P,
                              int rd, int rh, const float *spacing, int y_mode, float out_scale,
-                             int acc64, float *proj, float *samples) {
+                             int acc64, int seg_len, float *proj, float *samples) {
     for (int b = 0; b < B; ++b) {
         const float *V = vol + (size_t)b * d * w * h;
 #pragma omp parallel for collapse(2) schedule(dynamic, 8)
@@ -193,14 +196,20 @@ LRO_API void lro_drr_forward(const float *vol, int B, int d, int w, int h, const
                 for (int v = 0; v < rh; ++v) {
                     lro_ray r = ray_setup(poses + 3 * p, u, v, rd, rh, spacing);
                     size_t ray = ((size_t)p * rd + u) * rh + v;
-                    float acc = 0.0f; double acc_d = 0.0;
+                    float acc = 0.0f, run = 0.0f; double acc_d = 0.0;
                     for (int j = 0; j < w; ++j) {
                         float g[3];
                         ray_point(&r, j, d, w, h, y_mode, g);
                         /* flip (sdct:76): grid_sample x<-axis2 (W=h), y<-axis1 (H=w), z<-axis0 (D=d) */
                         float s = sample3(V, d, w, h, g[2], g[1], g[0], 0, 0);
                         if (samples && b == 0) samples[ray * w + j] = s;
-                        acc += s; acc_d += (double)s;
+                        acc_d += (double)s;
+                        if (seg_len > 0) {
+                            run += s;
+                            if ((j + 1) % seg_len == 0 || j == w - 1) { acc += run; run = 0.0f; }
+                        } else {
+                            acc += s;
+                        }
                     }
                     float sum = acc64 ? (float)acc_d : acc;
                     float o = sum * r.dx;

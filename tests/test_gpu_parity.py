@@ -71,8 +71,9 @@ def test_drr_small_vs_golden_and_oracle(dev):
     out = sdct.calculate_projection(g["vol"], g["poses"], g["resolution"], [1, 1, 1], tuple(g["spacing"]), dev)
     assert out.shape == g["proj"].shape and out.dtype == np.float32
     assert per_image_rel_l2(out, g["proj"]) <= TOL                       # reference (torch.sum cascade order)
-    ora = c_oracle.drr_forward(g["vol"], g["poses"], g["resolution"], g["spacing"])
-    assert np.array_equal(out, ora)                                      # same sequential fp32 ray sum: exact
+    ora = c_oracle.drr_forward(g["vol"], g["poses"], g["resolution"], g["spacing"],
+                               seg_len=c_oracle.kernel_seg_len(g["vol"].shape[1]))
+    assert np.array_equal(out, ora)                                      # same fp32 ray-segment sum order: exact
 
 
 def test_drr_csv_poses_and_anisotropic_spacing(dev):
@@ -108,7 +109,7 @@ def test_drr_ragged_shapes_vs_oracle(dev, shape, res, P):
     vol = rs.rand(2, *shape).astype(np.float32)
     poses = synthetic.wrapper_poses(50.0, P, shape[1])
     out = ops.drr_project(cu(vol, dev), poses, res, (2.0, 1.5, 3.0)).cpu().numpy()
-    ora = c_oracle.drr_forward(vol, poses, res, (2.0, 1.5, 3.0))
+    ora = c_oracle.drr_forward(vol, poses, res, (2.0, 1.5, 3.0), seg_len=c_oracle.kernel_seg_len(shape[1]))
     assert np.array_equal(out, ora)
 
 
@@ -130,7 +131,8 @@ def test_drr_per_item_poses_and_many_views(dev):
     poses = np.stack([synthetic.wrapper_poses(60.0, 70, 10), synthetic.wrapper_poses(40.0, 70, 10, 3.0)])
     out = ops.drr_project(cu(vol, dev), poses, (9, 8), (1.0, 1.0, 1.0)).cpu().numpy()
     for b in range(2):
-        assert np.array_equal(out[b], c_oracle.drr_forward(vol[b], poses[b], (9, 8), (1.0, 1.0, 1.0)))
+        assert np.array_equal(out[b], c_oracle.drr_forward(vol[b], poses[b], (9, 8), (1.0, 1.0, 1.0),
+                                                           seg_len=c_oracle.kernel_seg_len(10)))
 
 
 def test_drr_linearity_full_size(dev):
