@@ -35,17 +35,15 @@ __device__ __forceinline__ float div_const(float x, ConstDiv k) {
 }
 
 // floor(x) as float and int for |x| < 2^22, on the FP32/ALU pipes only.  FRND/F2I/I2F run on the XU pipe at 16
-// lanes/clk/SM and saturated it in the first version of these kernels (ncu: xu 95 %).  Adding 1.5*2^23 rounds x to
-// an integer that can be read straight out of the mantissa; one compare turns round-to-nearest into floor.
-// Callers clamp x to a few voxels around the volume first (samples further out have no in-bounds tap anyway).
+// lanes/clk/SM and saturated it in the first version of these kernels (ncu: xu 95 %).  Adding 1.5*2^23 (where one
+// ulp is 1) with round-toward-minus-infinity (FADD.RM) lands exactly on 1.5*2^23 + floor(x): the float floor is one
+// exact subtraction away and the integer floor sits in the mantissa.  Callers keep |x| < 2^22 (clamp / clip);
+// out-of-range or NaN inputs yield an int outside any realistic volume, which the bounds tests then reject.
 __device__ __forceinline__ void floor_fi(float x, float &f, int &i) {
     const float M = 12582912.0f;                  // 1.5 * 2^23 = 0x4B400000
-    const float t = __fadd_rn(x, M);
-    const float r = __fsub_rn(t, M);              // exact: nearest integer to x
-    const int ri = __float_as_int(t) - 0x4B400000;
-    const bool up = r > x;                        // rounded up -> step back
-    f = up ? __fsub_rn(r, 1.0f) : r;
-    i = up ? ri - 1 : ri;
+    const float t = __fadd_rd(x, M);
+    f = __fsub_rn(t, M);                          // exact
+    i = __float_as_int(t) - 0x4B400000;
 }
 // nearbyint(x) (half to even) for |x| < 2^22, same trick without the compare
 __device__ __forceinline__ int rint_i(float x) {
@@ -100,19 +98,16 @@ __device__ __forceinline__ f32x2 div_const2(f32x2 x, ConstDiv k) {
     const f32x2 r = fma2(splat2(-k.c), q0, x);
     return fma2(r, rc, q0);
 }
-// packed floor for two values with |x| < 2^22: float floors and int floors
+// packed floor for two values with |x| < 2^22: float floors and int floors (FADD2.RM, see floor_fi)
 __device__ __forceinline__ void floor2_fi(f32x2 x, f32x2 &f, int &i_lo, int &i_hi) {
     const f32x2 M = splat2(12582912.0f);
-    const f32x2 t = add2(x, M);
-    const f32x2 r = sub2(t, M);
-    float xl, xh, rl, rh, tl, th;
-    unpack2(x, xl, xh);
-    unpack2(r, rl, rh);
+    f32x2 t;
+    asm("add.rm.f32x2 %0, %1, %2;" : "=l"(t) : "l"(x), "l"(M));
+    f = sub2(t, M);
+    float tl, th;
     unpack2(t, tl, th);
-    const bool ul = rl > xl, uh = rh > xh;
-    f = pack2(ul ? __fsub_rn(rl, 1.0f) : rl, uh ? __fsub_rn(rh, 1.0f) : rh);
-    i_lo = __float_as_int(tl) - 0x4B400000 - (ul ? 1 : 0);
-    i_hi = __float_as_int(th) - 0x4B400000 - (uh ? 1 : 0);
+    i_lo = __float_as_int(tl) - 0x4B400000;
+    i_hi = __float_as_int(th) - 0x4B400000;
 }
 
 // Hides how a pointer was computed so that nvcc keeps it in a register pair instead of re-deriving it (as a 64-bit

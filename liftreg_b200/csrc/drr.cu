@@ -17,8 +17,14 @@ namespace lr {
 
 constexpr int DRR_MAX_VIEWS = 128;  // (volume, pose) pairs per launch; poses travel as kernel parameters
 constexpr int DRR_ROWS = 4;         // detector rows (u) per block in the one-ray-per-thread kernels (backward, grid)
-constexpr int DRR_PAIRS = 2;        // forward: ray pairs (2 detector rows each) per block along u
-constexpr int DRR_SEGS = 4;         // forward: every ray is cut into 4 runs of ceil(w/4) coronal planes, one warp each
+#ifndef LR_DRR_PAIRS
+#define LR_DRR_PAIRS 2
+#endif
+#ifndef LR_DRR_SEGS
+#define LR_DRR_SEGS 4
+#endif
+constexpr int DRR_PAIRS = LR_DRR_PAIRS;        // forward: ray pairs (2 detector rows each) per block along u
+constexpr int DRR_SEGS = LR_DRR_SEGS;         // forward: every ray is cut into 4 runs of ceil(w/4) coronal planes, one warp each
 
 struct DrrView {
     float sx, sy, sz;

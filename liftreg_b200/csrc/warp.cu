@@ -29,6 +29,7 @@ struct WarpDims {
     float hx, hy, hz;    // (W-1)/2, (H-1)/2, (D-1)/2
     float mx, my, mz;    // W-1, H-1, D-1
     double sp0, sp1, sp2;  // 1/(D-1), 1/(H-1), 1/(W-1) as float64 (identity map, net_utils.py:81)
+    float zero;          // +0.0f the compiler cannot constant-fold (see mul2_sep)
 };
 
 // ATen grid_sampler_unnormalize(align_corners) then optional clip_coordinates.
@@ -141,15 +142,16 @@ __device__ __forceinline__ void warp_pair(const float *__restrict__ src, float *
         // fails the test and takes the safe path.  The x axis is the one that diverges inside a warp (lanes run
         // along x, so only the lanes next to a face leave the volume): its two taps are predicated instead.  A
         // masked tap loads 0, and 0 * w added to the running sum changes nothing -- exactly ATen's "skip".
-        const float wlim = g.mx + 1.0f;
-        const bool ina = ixa > -1.0f && ixa < wlim && iya >= 0.0f && iya < g.my && iza >= 0.0f && iza < g.mz;
-        const bool inb = ixb > -1.0f && ixb < wlim && iyb >= 0.0f && iyb < g.my && izb >= 0.0f && izb < g.mz;
+        // The floors are taken first and the tests run on the integers: an out-of-range or NaN coordinate yields an
+        // index far outside any volume (see floor_fi), so no float pre-test / clamp is needed on this path.
+        f32x2 fx, fy, fz;
+        int x0a, x0b, y0a, y0b, z0a, z0b;
+        floor2_fi(ix, fx, x0a, x0b);
+        floor2_fi(iy, fy, y0a, y0b);
+        floor2_fi(iz, fz, z0a, z0b);
+        const bool ina = (unsigned)(x0a + 1) < (unsigned)(g.W + 1) && (unsigned)y0a < (unsigned)(g.H - 1) && (unsigned)z0a < (unsigned)(g.D - 1);
+        const bool inb = (unsigned)(x0b + 1) < (unsigned)(g.W + 1) && (unsigned)y0b < (unsigned)(g.H - 1) && (unsigned)z0b < (unsigned)(g.D - 1);
         if (ina && inb) {
-            f32x2 fx, fy, fz;
-            int x0a, x0b, y0a, y0b, z0a, z0b;
-            floor2_fi(ix, fx, x0a, x0b);
-            floor2_fi(iy, fy, y0a, y0b);
-            floor2_fi(iz, fz, z0a, z0b);
             const f32x2 wx1 = sub2(ix, fx), wx0 = sub2(add2(fx, one), ix);
             const f32x2 wy1 = sub2(iy, fy), wy0 = sub2(add2(fy, one), iy);
             const f32x2 wz1 = sub2(iz, fz), wz0 = sub2(add2(fz, one), iz);
@@ -161,7 +163,7 @@ __device__ __forceinline__ void warp_pair(const float *__restrict__ src, float *
             const int a0 = z0a * g.HW + y0a * g.W + x0a, b0 = z0b * g.HW + y0b * g.W + x0b;
             const int a1 = a0 + g.W, a2 = a0 + g.HW, a3 = a2 + g.W;
             const int b1 = b0 + g.W, b2 = b0 + g.HW, b3 = b2 + g.W;
-            const f32x2 half = splat2(0.5f), two = splat2(2.0f);
+            const f32x2 half = splat2(0.5f), two = splat2(2.0f), zero = splat2(g.zero);
 #pragma unroll 1
             for (int c = 0; c < nchan; ++c) {
                 const float *sc = opaque(src + (int64_t)c * g.nvox);
@@ -175,22 +177,18 @@ __device__ __forceinline__ void warp_pair(const float *__restrict__ src, float *
                 v[4] = pack2(LR_TAP(pa2, la), LR_TAP(pb2, lb)); v[5] = pack2(LR_TAP(pa2 + 1, ha), LR_TAP(pb2 + 1, hb));
                 v[6] = pack2(LR_TAP(pa3, la), LR_TAP(pb3, lb)); v[7] = pack2(LR_TAP(pa3 + 1, ha), LR_TAP(pb3 + 1, hb));
 #undef LR_TAP
-                // ATen: out += val * w per tap, product and sum rounded separately, in tap order.  ptxas contracts
-                // mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (a single rounding) whatever the flags, so the products
-                // are packed and the two running sums are scalar adds.
-                float ra = 0.0f, rb = 0.0f;
+                // ATen: out += val * w per tap, product and sum rounded separately, in tap order (mul2_sep keeps ptxas
+                // from contracting the pair into one FFMA2)
+                f32x2 acc = splat2(0.0f);
 #pragma unroll
                 for (int t = 0; t < 8; ++t) {
                     f32x2 val = v[t];
                     if (SCALE) val = mul2(add2(val, one), half);   // net_utils.py:50 (img+1)/2, fused per tap
-                    float pa, pb;
-                    unpack2(mul2(val, wt[t]), pa, pb);
-                    ra = add_rn(ra, pa);
-                    rb = add_rn(rb, pb);
+                    acc = add2(acc, mul2_sep(val, wt[t], zero));
                 }
-                if (SCALE) {                                       // net_utils.py:52 (x2 is exact: fusing is harmless)
-                    unpack2(sub2(mul2(pack2(ra, rb), two), one), ra, rb);
-                }
+                if (SCALE) acc = sub2(mul2(acc, two), one);        // net_utils.py:52 (x2 is exact: fusing is harmless)
+                float ra, rb;
+                unpack2(acc, ra, rb);
                 st_stream(dst + (int64_t)c * g.nvox_o + voxa, ra);
                 if (has_b) st_stream(dst + (int64_t)c * g.nvox_o + voxb, rb);
             }
@@ -370,6 +368,7 @@ static WarpDims make_dims(int C, int D, int H, int W, int z_begin = 0, int z_cou
     g.hx = (float)(W - 1) / 2.0f; g.hy = (float)(H - 1) / 2.0f; g.hz = (float)(D - 1) / 2.0f;
     g.mx = (float)(W - 1); g.my = (float)(H - 1); g.mz = (float)(D - 1);
     g.sp0 = 1.0 / (double)(D - 1); g.sp1 = 1.0 / (double)(H - 1); g.sp2 = 1.0 / (double)(W - 1);
+    g.zero = 0.0f;
     return g;
 }
 
@@ -377,6 +376,7 @@ static int check_warp_args(int B, int C, int D, int H, int W, int padding, int m
     LR_REQUIRE(B > 0 && C > 0 && D > 0 && H > 0 && W > 0, "warp: non-positive dimension (B=%d C=%d D=%d H=%d W=%d)", B, C, D, H, W);
     LR_REQUIRE((int64_t)D * H * W < (1ll << 31) - 2 * (int64_t)H * W - 4, "warp: D*H*W must fit 32-bit voxel offsets");
     LR_REQUIRE(D < 65536 && (H + WARP_TY - 1) / WARP_TY <= 65535, "warp: D and H/8 must be < 65536 (grid limits)");
+    LR_REQUIRE(W < (1 << 21) && H < (1 << 21), "warp: H and W must be < 2^21 (mantissa floor)");
     LR_REQUIRE(padding == LR_PAD_ZEROS || padding == LR_PAD_BORDER, "warp: padding must be 0 (zeros) or 1 (border)");
     LR_REQUIRE(mode == LR_MODE_LINEAR || mode == LR_MODE_NEAREST, "warp: mode must be 0 (linear) or 1 (nearest)");
     return LR_OK;

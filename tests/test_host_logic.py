@@ -25,21 +25,27 @@ def test_markstein_division_by_constant_is_correctly_rounded():
 
 
 def test_magic_number_floor_matches_floor():
-    """common.cuh floor_fi: t = x + 1.5*2^23; r = t - 1.5*2^23; floor = r - (r > x); int from the mantissa of t."""
+    """common.cuh floor_fi: t = x + 1.5*2^23 rounded toward -inf (FADD.RM); floor = t - 1.5*2^23; the integer floor is
+    the mantissa of t.  rint_i is the round-to-nearest variant."""
     rs = np.random.RandomState(1)
     xs = np.concatenate([rs.uniform(-3, 600, 2_000_000), np.arange(-8, 600, 0.25), np.arange(-2, 3, 2.0 ** -20),
-                         [-2.0, -1.0, -0.0, 0.0, 0.99999994, 1.0, 511.99997, 512.0]]).astype(f32)
+                         [-2.0, -1.0, -0.0, 0.0, 0.99999994, 1.0, 511.99997, 512.0, -4194303.5, 4194303.5]]).astype(f32)
     M = f32(12582912.0)
-    t = (xs + M).astype(f32)
-    r = (t - M).astype(f32)
-    ri = t.view(np.int32) - np.int32(0x4B400000)
-    up = r > xs
-    fl = np.where(up, r - f32(1), r)
-    fi = np.where(up, ri - 1, ri)
+    exact = xs.astype(np.float64) + np.float64(M)            # exact in float64
+    t = exact.astype(f32)
+    t = np.where(t.astype(np.float64) > exact, np.nextafter(t, f32(-np.inf)), t)   # round toward -inf
+    fl = (t - M).astype(f32)
+    fi = t.view(np.int32) - np.int32(0x4B400000)
     assert np.array_equal(fl, np.floor(xs))
     assert np.array_equal(fi, np.floor(xs).astype(np.int32))
-    # nearest (half to even) variant
-    assert np.array_equal(ri, np.rint(xs).astype(np.int32))
+    # out-of-range and NaN inputs give indices no bounds test accepts (|i| >= 2^22)
+    bad = np.array([4194304.0, 1e7, 3e9, -4194304.5, -1e7, -3e9, np.nan, np.inf, -np.inf], f32)
+    with np.errstate(invalid="ignore", over="ignore"):
+        tb = (bad.astype(np.float64) + np.float64(M)).astype(f32)
+    ib = tb.view(np.int32).astype(np.int64) - 0x4B400000
+    assert np.all((ib < 0) | (ib >= (1 << 22)))
+    tn = (xs + M).astype(f32)                                  # round to nearest even
+    assert np.array_equal(tn.view(np.int32) - np.int32(0x4B400000), np.rint(xs).astype(np.int32))
 
 
 def test_scaling_identities_used_to_fold_constants():
