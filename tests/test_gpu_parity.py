@@ -519,3 +519,73 @@ def test_model_hot_path_drop_in(dev):
     assert torch.equal(phi.cpu(), ref_phi) and torch.equal(warped.cpu(), ref_warped)
     fused = ops.warp(cu(moving, dev), cu(disp, dev), zero_boundary=True, using_scale=True, disp_plus_identity=True)
     assert torch.equal(fused.cpu(), ref_warped)
+
+
+# ------------------------------------------------------------------ maximum sizes (BASELINE configs[3] geometry)
+def test_drr_cfg4_geometry_512_cubed(dev):
+    """512^3 volume, 512^2 detector (the preprocessing sweep of configs[3]): two of the 64 views exactly against the
+    oracle, and all 64 views through size-independent properties (finite, non-negative, view symmetry)."""
+    from liftreg_b200 import ops, synthetic
+    from oracle import c_oracle
+    n = 512
+    z = np.arange(n, dtype=np.float32)
+    vol = (0.1 + 0.05 * np.sin(z / 13.0)[:, None, None] * np.cos(z / 17.0)[None, :, None]
+           + 0.04 * np.sin(z / 11.0)[None, None, :]).astype(np.float32)
+    poses = synthetic.wrapper_poses(60.0, 64, n)
+    tv = cu(vol[None], dev)
+    out = ops.drr_project(tv, poses, (512, 512), (1.0, 1.0, 1.0))
+    assert out.shape == (1, 64, 512, 512)
+    o = out[0].cpu().numpy()
+    assert np.isfinite(o).all() and (o >= 0).all() and o.max() > 1.0
+    sel = [0, 37]
+    ora = c_oracle.drr_forward(vol, poses[sel], (512, 512), (1.0, 1.0, 1.0), seg_len=c_oracle.kernel_seg_len(n))
+    assert np.array_equal(o[sel], ora)
+    # the same volume projected with view-sharded launches (8 views per call, as 8 GPUs would) is identical
+    parts = [ops.drr_project(tv, poses[i:i + 8], (512, 512), (1.0, 1.0, 1.0)) for i in range(0, 64, 8)]
+    assert torch.equal(torch.cat(parts, dim=1), out)
+
+
+def test_warp_and_backprojection_320_cubed_vs_oracle(dev):
+    """Larger-than-benchmark volume (8x the voxels of 160^3) with batch 2: exact against the oracle."""
+    from liftreg_b200 import ops, synthetic
+    from oracle import c_oracle
+    shape = (320, 320, 320)
+    rs = np.random.RandomState(40)
+    img = rs.uniform(-1, 1, (1, 1) + shape).astype(np.float32)
+    disp = synthetic.smooth_displacement(shape, seed=4, max_disp=0.03, coarse=6)[None]
+    phi = (disp + synthetic.identity_map_np(shape)[None]).astype(np.float32)
+    out = ops.warp(cu(img, dev), cu(phi, dev), zero_boundary=True, using_scale=True).cpu().numpy()
+    assert np.array_equal(out, c_oracle.warp_forward(img, phi, True, True, "bilinear"))
+    tp = rs.uniform(-1, 1, (2, 2, 512, 512)).astype(np.float32)
+    poses = synthetic.wrapper_poses(60.0, 2, shape[1]).astype(np.float32)
+    vol = ops.backproject(cu(tp, dev), poses, shape).cpu().numpy()
+    assert np.array_equal(vol, c_oracle.backproject_forward(tp, poses, shape))
+
+
+def test_remaining_mirror_entry_points(dev):
+    """forward_grids*, backproj_grids (old fixed geometry), calc_relative_atten_coef_cuda, DRRProjector reuse."""
+    from liftreg_b200 import sdct_projection_utils as sdct, synthetic
+    from oracle import c_oracle
+    shp = (10, 18, 12)
+    sp = torch.tensor([2.2, 1.7, 2.5])
+    poses = synthetic.wrapper_poses(60.0, 3, shp[1], 3.0)
+    grids, dx = sdct.forward_grids(60.0, 3, sp, shp, device=dev)
+    og, odx = c_oracle.project_grid(poses, (15, 18), shp, sp.numpy())
+    assert np.array_equal(grids.cpu().numpy(), og[..., ::-1]) and np.array_equal(dx.cpu().numpy(), odx)
+    grids2, _ = sdct.forward_grids_with_poses(poses, sp, shp, device=dev, receptor_size=(7, 9))
+    assert np.array_equal(grids2.cpu().numpy(), c_oracle.project_grid(poses, (7, 9), shp, sp.numpy())[0][..., ::-1])
+    g = load_golden("backproj_grids_old")
+    old = sdct.backproj_grids(float(g["scan_range"]), int(g["proj_num"]), tuple(g["img_shape"]), tuple(g["proj_shape"]), device=dev)
+    assert np.abs(old.cpu().numpy() - g["grid"]).max() <= 2e-6
+    a = load_golden("atten")
+    t = cu(a["hu"].copy(), dev)
+    mu = sdct.calc_relative_atten_coef_cuda(t)
+    assert np.array_equal(mu.cpu().numpy(), a["mu"]) and float(t.min()) >= -1000.0
+    # projector object reuses its buffers across calls of different sizes
+    pr = sdct.DRRProjector(dev)
+    d1 = load_golden("drr_small")
+    for _ in range(2):
+        o = pr.project_numpy(d1["vol"], d1["poses"], d1["resolution"], d1["spacing"])
+        assert per_image_rel_l2(o, d1["proj"]) <= TOL
+    d2 = load_golden("drr_small_csvposes")
+    assert per_image_rel_l2(pr.project_numpy(d2["vol"], d2["poses"], d2["resolution"], d2["spacing"]), d2["proj"]) <= TOL

@@ -19,8 +19,13 @@ VOL, DET, P, R = (160, 160, 160), (256, 256), 4, 8
 
 
 def main():
-    which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["warp", "backproject", "drr"]
-    iters = int(sys.argv[sys.argv.index("--iters") + 1]) if "--iters" in sys.argv else 2000
+    iters = 2000
+    args = list(sys.argv[1:])
+    if "--iters" in args:
+        k = args.index("--iters")
+        iters = int(args[k + 1])
+        del args[k:k + 2]
+    which = args or ["warp", "backproject", "drr"]
     dev = torch.device("cuda:0")
     lib = _native.lib()
     stream = torch.cuda.Stream()
@@ -50,7 +55,22 @@ def main():
         _native.check(lib.lr_drr_forward(vp(s["mu"]), 1, *VOL, ops._dp(p64), 1, P, 240, 240, ops._fp(sp3), 0,
                                          ctypes.c_float(0.1), vp(s["drr"]), st), "drr")
 
-    units = {"warp": (k_warp, nv, 20 * nv), "backproject": (k_backproject, P * nv, 4 * P * nv + 4 * P * DET[0] * DET[1]),
+    gout = torch.from_numpy(rs.standard_normal((1, 1) + VOL).astype(np.float32)).to(dev)
+    gphi = [torch.empty((1, 3) + VOL, device=dev) for _ in range(R)]
+    gdrr = torch.from_numpy(rs.standard_normal((1, P, 240, 240)).astype(np.float32)).to(dev)
+    gvol = [torch.zeros((1,) + VOL, device=dev) for _ in range(R)]
+    for i, s_ in enumerate(sets):
+        s_["gphi"], s_["gvol"] = gphi[i], gvol[i]
+
+    def k_warp_bwd(s, st):     # d/dphi only (what training needs: LiftRegDeformSubspaceBackproj.py:69 with moving as data)
+        _native.check(lib.lr_warp_backward(vp(gout), vp(s["moving"]), vp(s["phi"]), 1, 1, *VOL, 0, 0, 1, 0, None, vp(s["gphi"]), st), "warp_bwd")
+
+    def k_drr_bwd(s, st):
+        _native.check(lib.lr_drr_backward(vp(gdrr), 1, *VOL, ops._dp(p64), 1, P, 240, 240, ops._fp(sp3), 0,
+                                          ctypes.c_float(0.1), vp(s["gvol"]), st), "drr_bwd")
+
+    units = {"warp": (k_warp, nv, 20 * nv), "warp_bwd": (k_warp_bwd, nv, 32 * nv),
+             "drr_bwd": (k_drr_bwd, P * 240 * 240 * VOL[1], 4 * nv + 4 * P * 240 * 240), "backproject": (k_backproject, P * nv, 4 * P * nv + 4 * P * DET[0] * DET[1]),
              "drr": (k_drr, P * 240 * 240 * VOL[1], 4 * nv + 4 * P * 240 * 240)}
     for name in which:
         fn, n_units, nbytes = units[name]
