@@ -335,6 +335,153 @@ __global__ void __launch_bounds__(WARP_TX * WARP_TY)
     }
 }
 
+// d(warp)/d(phi) only, zeros padding: what a training step needs (the moving image is data, model :69).  Same
+// two-voxels-per-thread packed layout as the forward kernel.  The gradient is a gather, so it is deterministic; it is
+// evaluated in a factorised form (differences of x/y/z-adjacent taps times precomputed weight*grad products, with
+// fused multiply-adds), which differs from ATen's expression order by fp32 round-off only (tests: <= 2e-5 rel-L2).
+template <bool SCALE>
+__device__ __forceinline__ void warp_bwd_phi_one(const float *__restrict__ gout_b, const float *__restrict__ img_b,
+                                                 float *__restrict__ gp, const WarpDims &g, int vox, float ix, float iy,
+                                                 float iz) {
+    ix = clamp_index(ix, g.mx + 2.0f); iy = clamp_index(iy, g.my + 2.0f); iz = clamp_index(iz, g.mz + 2.0f);
+    float fx, fy, fz;
+    int x0, y0, z0;
+    floor_fi(ix, fx, x0);
+    floor_fi(iy, fy, y0);
+    floor_fi(iz, fz, z0);
+    const float wx[2] = {sub_rn(add_rn(fx, 1.0f), ix), sub_rn(ix, fx)};
+    const float wy[2] = {sub_rn(add_rn(fy, 1.0f), iy), sub_rn(iy, fy)};
+    const float wz[2] = {sub_rn(add_rn(fz, 1.0f), iz), sub_rn(iz, fz)};
+    const int base = z0 * g.HW + y0 * g.W + x0;
+    float gix = 0.0f, giy = 0.0f, giz = 0.0f;
+    for (int c = 0; c < g.C; ++c) {
+        float go = ld_stream(gout_b + (int64_t)c * g.nvox_o + vox);
+        if (SCALE) go = mul_rn(go, 2.0f);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const int tx = t & 1, ty = (t >> 1) & 1, tz = t >> 2;
+            const bool ok = (unsigned)(x0 + tx) < (unsigned)g.W && (unsigned)(y0 + ty) < (unsigned)g.H &&
+                            (unsigned)(z0 + tz) < (unsigned)g.D;
+            if (!ok) continue;
+            float val = __ldg(img_b + (int64_t)c * g.nvox + base + tx + ty * g.W + tz * g.HW);
+            if (SCALE) val = mul_rn(add_rn(val, 1.0f), 0.5f);
+            const float tx_ = mul_rn(mul_rn(mul_rn(val, wy[ty]), wz[tz]), go);
+            const float ty_ = mul_rn(mul_rn(mul_rn(val, wx[tx]), wz[tz]), go);
+            const float tz_ = mul_rn(mul_rn(mul_rn(val, wx[tx]), wy[ty]), go);
+            gix = tx ? add_rn(gix, tx_) : sub_rn(gix, tx_);
+            giy = ty ? add_rn(giy, ty_) : sub_rn(giy, ty_);
+            giz = tz ? add_rn(giz, tz_) : sub_rn(giz, tz_);
+        }
+    }
+    st_stream(gp + vox, mul_rn(g.hz, giz));
+    st_stream(gp + g.nvox_o + vox, mul_rn(g.hy, giy));
+    st_stream(gp + 2 * (int64_t)g.nvox_o + vox, mul_rn(g.hx, gix));
+}
+
+template <bool SCALE, bool IDENT>
+__global__ void __launch_bounds__(WARP_TX * WARP_TY)
+    warp_backward_phi_kernel(const float *__restrict__ gout, const float *__restrict__ img, const float *__restrict__ phi,
+                             float *__restrict__ gphi, WarpDims g) {
+    __shared__ IdentTable<WARP_TY * WARP_VY> ident;
+    const int x = blockIdx.x * WARP_TX + threadIdx.x;
+    const int ya = blockIdx.y * (WARP_TY * WARP_VY) + threadIdx.y;
+    const int b = g.zblocks == 1 ? (int)blockIdx.z : (int)__umulhi(blockIdx.z, g.z_magic);
+    const int z = blockIdx.z - b * g.Do;
+    if (IDENT) build_ident_table(ident, g, blockIdx.x * WARP_TX, blockIdx.y * (WARP_TY * WARP_VY), z + g.z_off);
+    if (x >= g.W || ya >= g.H) return;
+    const bool has_b = ya + WARP_TY < g.H;
+    const int yb = has_b ? ya + WARP_TY : ya;
+    const int voxa = z * g.HW + ya * g.W + x, voxb = z * g.HW + yb * g.W + x;
+
+    const float *p0 = opaque(phi + (int64_t)b * 3 * g.nvox_o);
+    const float *p1 = opaque(p0 + g.nvox_o);
+    const float *p2 = opaque(p1 + g.nvox_o);
+    f32x2 gz = pack2(ld_stream(p0 + (unsigned)voxa), ld_stream(p0 + (unsigned)voxb));
+    f32x2 gy = pack2(ld_stream(p1 + (unsigned)voxa), ld_stream(p1 + (unsigned)voxb));
+    f32x2 gx = pack2(ld_stream(p2 + (unsigned)voxa), ld_stream(p2 + (unsigned)voxb));
+    if (IDENT) {
+        gz = add2(gz, splat2(ident.z));
+        gy = add2(gy, pack2(ident.y[threadIdx.y], ident.y[has_b ? threadIdx.y + WARP_TY : threadIdx.y]));
+        gx = add2(gx, splat2(ident.x[threadIdx.x]));
+    }
+    const f32x2 one = splat2(1.0f);
+    const f32x2 ix = mul2(add2(gx, one), splat2(g.hx)), iy = mul2(add2(gy, one), splat2(g.hy)), iz = mul2(add2(gz, one), splat2(g.hz));
+    const float *gout_b = opaque(gout + (int64_t)b * g.C * g.nvox_o);
+    const float *img_b = opaque(img + (int64_t)b * g.C * g.nvox);
+    float *gp = opaque(gphi + (int64_t)b * 3 * g.nvox_o);
+
+    f32x2 fx, fy, fz;
+    int x0a, x0b, y0a, y0b, z0a, z0b;
+    floor2_fi(ix, fx, x0a, x0b);
+    floor2_fi(iy, fy, y0a, y0b);
+    floor2_fi(iz, fz, z0a, z0b);
+    // packed path: y/z tap pairs inside, at least one x tap inside (the x taps are predicated: lanes run along x, so
+    // the faces x = 0 / W-1 are where a warp would otherwise diverge); a masked tap reads as intensity 0 = skipped
+    const bool ina = (unsigned)(x0a + 1) < (unsigned)(g.W + 1) && (unsigned)y0a < (unsigned)(g.H - 1) && (unsigned)z0a < (unsigned)(g.D - 1);
+    const bool inb = (unsigned)(x0b + 1) < (unsigned)(g.W + 1) && (unsigned)y0b < (unsigned)(g.H - 1) && (unsigned)z0b < (unsigned)(g.D - 1);
+    if (!(ina && inb)) {
+        float ixa, ixb, iya, iyb, iza, izb;
+        unpack2(ix, ixa, ixb); unpack2(iy, iya, iyb); unpack2(iz, iza, izb);
+        warp_bwd_phi_one<SCALE>(gout_b, img_b, gp, g, voxa, ixa, iya, iza);
+        if (has_b) warp_bwd_phi_one<SCALE>(gout_b, img_b, gp, g, voxb, ixb, iyb, izb);
+        return;
+    }
+    const f32x2 wx1 = sub2(ix, fx), wx0 = sub2(add2(fx, one), ix);
+    const f32x2 wy1 = sub2(iy, fy), wy0 = sub2(add2(fy, one), iy);
+    const f32x2 wz1 = sub2(iz, fz), wz0 = sub2(add2(fz, one), iz);
+    const bool la = x0a >= 0, ha = x0a < g.W - 1, lb = x0b >= 0, hb = x0b < g.W - 1;   // x taps inside?
+    const int a0 = z0a * g.HW + y0a * g.W + x0a, b0 = z0b * g.HW + y0b * g.W + x0b;      // signed: x0 may be -1
+    const int a1 = a0 + g.W, a2 = a0 + g.HW, a3 = a2 + g.W;
+    const int b1 = b0 + g.W, b2 = b0 + g.HW, b3 = b2 + g.W;
+    const f32x2 half = splat2(0.5f);
+    f32x2 gix = splat2(0.0f), giy = splat2(0.0f), giz = splat2(0.0f);
+#pragma unroll 1
+    for (int c = 0; c < g.C; ++c) {
+        const float *sc = opaque(img_b + (int64_t)c * g.nvox);
+        const float *goc = gout_b + (int64_t)c * g.nvox_o;
+        f32x2 go = pack2(ld_stream(goc + (unsigned)voxa), ld_stream(goc + (unsigned)voxb));
+        if (SCALE) go = mul2(go, splat2(2.0f));
+        const float *pa0 = sc + a0, *pa1 = sc + a1, *pa2 = sc + a2, *pa3 = sc + a3;
+        const float *pb0 = sc + b0, *pb1 = sc + b1, *pb2 = sc + b2, *pb3 = sc + b3;
+        f32x2 v[8];     // tap index t = tx + 2 ty + 4 tz
+#define LR_TAP(p, ok) ((ok) ? __ldg(p) : (SCALE ? -1.0f : 0.0f))
+        v[0] = pack2(LR_TAP(pa0, la), LR_TAP(pb0, lb)); v[1] = pack2(LR_TAP(pa0 + 1, ha), LR_TAP(pb0 + 1, hb));
+        v[2] = pack2(LR_TAP(pa1, la), LR_TAP(pb1, lb)); v[3] = pack2(LR_TAP(pa1 + 1, ha), LR_TAP(pb1 + 1, hb));
+        v[4] = pack2(LR_TAP(pa2, la), LR_TAP(pb2, lb)); v[5] = pack2(LR_TAP(pa2 + 1, ha), LR_TAP(pb2 + 1, hb));
+        v[6] = pack2(LR_TAP(pa3, la), LR_TAP(pb3, lb)); v[7] = pack2(LR_TAP(pa3 + 1, ha), LR_TAP(pb3 + 1, hb));
+#undef LR_TAP
+        if (SCALE) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) v[t] = mul2(add2(v[t], one), half);
+        }
+        // d/dx: sum over (ty,tz) of (v[1,ty,tz] - v[0,ty,tz]) * wy*wz * go, and likewise for y and z.  The pairwise
+        // weight products are formed on the fly (keeping 12 more packed values live would cost occupancy).
+        const f32x2 wxs[2] = {wx0, wx1}, wys[2] = {wy0, wy1}, wzs[2] = {wz0, wz1};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int ty = q & 1, tz = q >> 1;
+            gix = fma2(sub2(v[1 + 2 * ty + 4 * tz], v[0 + 2 * ty + 4 * tz]), mul2(mul2(wys[ty], wzs[tz]), go), gix);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int tx = q & 1, tz = q >> 1;
+            giy = fma2(sub2(v[tx + 2 + 4 * tz], v[tx + 4 * tz]), mul2(mul2(wxs[tx], wzs[tz]), go), giy);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int tx = q & 1, ty = q >> 1;
+            giz = fma2(sub2(v[tx + 2 * ty + 4], v[tx + 2 * ty]), mul2(mul2(wxs[tx], wys[ty]), go), giz);
+        }
+    }
+    float ra, rb;
+    unpack2(mul2(splat2(g.hz), giz), ra, rb);
+    st_stream(gp + (unsigned)voxa, ra); if (has_b) st_stream(gp + (unsigned)voxb, rb);
+    unpack2(mul2(splat2(g.hy), giy), ra, rb);
+    st_stream(gp + g.nvox_o + voxa, ra); if (has_b) st_stream(gp + g.nvox_o + voxb, rb);
+    unpack2(mul2(splat2(g.hx), gix), ra, rb);
+    st_stream(gp + 2 * (int64_t)g.nvox_o + voxa, ra); if (has_b) st_stream(gp + 2 * (int64_t)g.nvox_o + voxb, rb);
+}
+
 __global__ void __launch_bounds__(WARP_TX * WARP_TY) identity_map_kernel(float *__restrict__ out, WarpDims g) {
     __shared__ IdentTable<WARP_TY> ident;
     const int x = blockIdx.x * WARP_TX + threadIdx.x;
@@ -490,7 +637,18 @@ extern "C" int lr_warp_backward_slab(const float *grad_out, const float *img, co
         const dim3 grid = warp_grid(nb, g.Do, H, W);
         const int64_t io = (int64_t)b0 * C * g.nvox, oo = (int64_t)b0 * C * g.nvox_o, po = (int64_t)b0 * 3 * g.nvox_o;
         float *gi = grad_img ? grad_img + io : nullptr, *gp = grad_phi ? grad_phi + po : nullptr;
-        if (padding == LR_PAD_ZEROS) launch_bwd<LR_PAD_ZEROS>(sc, id, grid, st, grad_out + oo, img + io, phi + po, gi, gp, g);
+        if (padding == LR_PAD_ZEROS && !gi) {
+            // training configuration: map gradient only -> packed two-voxel kernel
+            const dim3 grid2 = warp_grid(nb, g.Do, H, W, WARP_VY);
+            const dim3 blk(WARP_TX, WARP_TY);
+            if (sc) {
+                if (id) warp_backward_phi_kernel<true, true><<<grid2, blk, 0, st>>>(grad_out + oo, img + io, phi + po, gp, g);
+                else warp_backward_phi_kernel<true, false><<<grid2, blk, 0, st>>>(grad_out + oo, img + io, phi + po, gp, g);
+            } else {
+                if (id) warp_backward_phi_kernel<false, true><<<grid2, blk, 0, st>>>(grad_out + oo, img + io, phi + po, gp, g);
+                else warp_backward_phi_kernel<false, false><<<grid2, blk, 0, st>>>(grad_out + oo, img + io, phi + po, gp, g);
+            }
+        } else if (padding == LR_PAD_ZEROS) launch_bwd<LR_PAD_ZEROS>(sc, id, grid, st, grad_out + oo, img + io, phi + po, gi, gp, g);
         else launch_bwd<LR_PAD_BORDER>(sc, id, grid, st, grad_out + oo, img + io, phi + po, gi, gp, g);
         if (int e = check_launch("warp_backward_kernel")) return e;
     }
