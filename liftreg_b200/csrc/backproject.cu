@@ -35,7 +35,7 @@ struct BpDims {
     int ichunk;                    // planes per block: ceil(d / ceil(d / BP_ICHUNK)) <= BP_ICHUNK
     int p0;                        // first view of this launch
     float half_d, half_h;          // d/2, h/2 (exact)
-    float pwf, phf;                // (float)pw, (float)ph
+    ConstDiv div_pw, div_ph;       // division by (float)pw, (float)ph via Markstein (bit-identical to IEEE division)
     float hpw, hph;                // (pw-1)/2, (ph-1)/2
     int64_t proj_view_stride;      // pw*ph
     int64_t out_batch_stride, out_chan_stride;
@@ -47,9 +47,9 @@ struct AxisTap {      // one axis of the bilinear footprint
 };
 
 // normalised coordinate -> (floor index, upper weight), ATen vector-kernel order
-__device__ __forceinline__ AxisTap axis_tap(float centred, float s_c, float scale, float sizef, float half_sm1) {
+__device__ __forceinline__ AxisTap axis_tap(float centred, float s_c, float scale, ConstDiv size, float half_sm1) {
     float a = add_rn(mul_rn(sub_rn(centred, s_c), scale), s_c);   // (x - s)*scale + s
-    float g = mul_rn(div_rn(a, sizef), 2.0f);                     // / size * 2
+    float g = mul_rn(div_const(a, size), 2.0f);                   // / size * 2
     float ix = mul_rn(add_rn(g, 1.0f), half_sm1);                 // (g+1)*((S-1)/2)
     ix = clamp_index(ix, half_sm1 * 2.0f + 3.0f);                 // beyond [-2, S+1] no tap is in bounds
     float fl;
@@ -73,12 +73,20 @@ struct __align__(16) BpRow {
                   // bit 3 = moved further or first plane (fetch both rows), bit 4 = upper row must be fetched
 };
 
-// Builds the table; returns (block-uniformly) whether every plane of the chunk has both rows inside the detector.
-__device__ __forceinline__ bool build_row_table(BpRow *rows, const BpDims &g, int i_begin, int i_count, float sx,
-                                                float scale) {
+// Compact entry for the fast path (all rows valid, so off0 >= 0): one LDS.64 instead of an LDS.128 -- a warp-wide
+// broadcast LDS.128 costs ~4 L1 wavefronts, which made the table read as expensive as the gathers (ncu:
+// l1tex__data_pipe_lsu_wavefronts_mem_shared = 38 % of all wavefronts).
+struct __align__(8) BpRow8 {
+    float n;        // iy - floor(iy); s = 1 - n is recomputed
+    int packed;     // (off0 << 5) | window flags (bits 2..4 of BpRow::mask)
+};
+
+// Builds the tables; returns (block-uniformly) whether every plane of the chunk has both rows inside the detector.
+__device__ __forceinline__ bool build_row_table(BpRow *rows, BpRow8 *rows8, const BpDims &g, int i_begin, int i_count,
+                                                float sx, float scale) {
     int ok = 1;
     for (int t_idx = threadIdx.x; t_idx < i_count; t_idx += blockDim.x) {
-        AxisTap t = axis_tap((float)(g.i_off + i_begin + t_idx) - g.half_d, sx, scale, g.pwf, g.hpw);
+        AxisTap t = axis_tap((float)(g.i_off + i_begin + t_idx) - g.half_d, sx, scale, g.div_pw, g.hpw);
         BpRow r;
         r.off0 = t.i0 * g.ph;
         r.n = t.w1;
@@ -88,12 +96,18 @@ __device__ __forceinline__ bool build_row_table(BpRow *rows, const BpDims &g, in
         // consecutive planes advance the detector row by ~1..1.4 (the magnification): tell the consumer how far
         int step = 2;
         if (t_idx > 0) {
-            const AxisTap tp = axis_tap((float)(g.i_off + i_begin + t_idx - 1) - g.half_d, sx, scale, g.pwf, g.hpw);
+            const AxisTap tp = axis_tap((float)(g.i_off + i_begin + t_idx - 1) - g.half_d, sx, scale, g.div_pw, g.hpw);
             const int dlt = t.i0 - tp.i0;
             step = (dlt == 0 || dlt == 1) ? dlt : 2;
         }
         r.mask |= step == 1 ? (4 | 16) : (step == 0 ? 0 : (8 | 16));
         rows[t_idx] = r;
+        if (rows8) {
+            BpRow8 c;
+            c.n = r.n;
+            c.packed = (int)(((unsigned)r.off0 << 5) | (unsigned)(r.mask & 28));
+            rows8[t_idx] = c;
+        }
     }
     return __syncthreads_and(ok) != 0;
 }
@@ -107,20 +121,30 @@ __device__ __forceinline__ float bilerp(float va, float vb, float vc, float vd, 
 __global__ void __launch_bounds__(256)
     backproject_forward_kernel(const float *__restrict__ proj, float *__restrict__ out, BpDims g, BpPoses poses) {
     __shared__ BpRow rows[BP_ICHUNK];
+    __shared__ BpRow8 rows8[BP_ICHUNK];
 
     const int j = blockIdx.x;
     const int i_begin = blockIdx.y * g.ichunk;
     const int pl = blockIdx.z;           // view inside this launch
     const int p = g.p0 + pl;
     const float sx = poses.s[pl][0], sy = poses.s[pl][1], sz = poses.s[pl][2];
-    const float scale = view_scale(sy, g.w, j);
     const int i_count = min(g.ichunk, g.d - i_begin);
-    const bool rows_ok = build_row_table(rows, g, i_begin, i_count, sx, scale);
+    // Block set-up used to cost as much as the sample loop (ablation: 11.7 of 25.6 us with the loop removed): every
+    // thread ran three IEEE divisions.  Now the only true division (scale = sy / (sy - y_j), block-uniform) is done by
+    // the table-building threads and broadcast through shared memory; /pw and /ph are Markstein multiplications.
+    __shared__ float s_scale;
+    float scale = 0.0f;
+    if ((int)threadIdx.x < i_count || threadIdx.x == 0) {
+        scale = view_scale(sy, g.w, j);
+        if (threadIdx.x == 0) s_scale = scale;
+    }
+    const bool rows_ok = build_row_table(rows, rows8, g, i_begin, i_count, sx, scale);
+    scale = s_scale;
 
     const int64_t proj_batch = (int64_t)g.P * g.proj_view_stride;
     const int64_t plane_bytes = (int64_t)g.w * g.h * 4;
     for (int k = threadIdx.x; k < g.h; k += blockDim.x) {
-        const AxisTap tv = axis_tap((float)k - g.half_h, sz, scale, g.phf, g.hph);
+        const AxisTap tv = axis_tap((float)k - g.half_h, sz, scale, g.div_ph, g.hph);
         const float wq = tv.w1, e = sub_rn(1.0f, wq);
         const bool c0 = (unsigned)tv.i0 < (unsigned)g.ph, c1 = (unsigned)(tv.i0 + 1) < (unsigned)g.ph;
         // geometry (table + v-part) is shared by all batch items; the batch loop is the outer one so that the
@@ -142,19 +166,20 @@ __global__ void __launch_bounds__(256)
                 const f32x2 e2 = splat2(e), w2 = splat2(wq);
 #pragma unroll 4
                 for (int ii = 0; ii < i_count; ++ii) {
-                    const BpRow r = rows[ii];
-                    if (r.mask & 4) { va = vc; vb = vd; }     // moved exactly one row down: reuse the upper row
-                    if (r.mask & 8) {                         // moved further (or first plane): fetch the lower row too
-                        const float *q0 = base + (unsigned)r.off0;
+                    const BpRow8 r = rows8[ii];
+                    const unsigned off0 = (unsigned)r.packed >> 5;
+                    if (r.packed & 4) { va = vc; vb = vd; }   // moved exactly one row down: reuse the upper row
+                    if (r.packed & 8) {                       // moved further (or first plane): fetch the lower row too
+                        const float *q0 = base + off0;
                         va = __ldg(q0); vb = __ldg(q0 + 1);
                     }
-                    if (r.mask & 16) {
-                        const float *q1 = base + (unsigned)(r.off0 + g.ph);
+                    if (r.packed & 16) {
+                        const float *q1 = base + (off0 + (unsigned)g.ph);
                         vc = __ldg(q1); vd = __ldg(q1 + 1);
                     }
                     // weights (n,s) x e and (n,s) x w as two packed products: (sw, nw) and (se, ne)
                     float sw, nw, se, ne;
-                    const f32x2 ns = pack2(r.n, r.s);
+                    const f32x2 ns = pack2(r.n, sub_rn(1.0f, r.n));
                     unpack2(mul2(ns, e2), sw, nw);
                     unpack2(mul2(ns, w2), se, ne);
                     st_stream((float *)o, fma_rn(vd, se, fma_rn(vc, sw, fma_rn(vb, ne, mul_rn(va, nw)))));
@@ -188,12 +213,12 @@ __global__ void __launch_bounds__(256)
     const float sx = poses.s[pl][0], sy = poses.s[pl][1], sz = poses.s[pl][2];
     const float scale = view_scale(sy, g.w, j);
     const int i_count = min(g.ichunk, g.d - i_begin);
-    build_row_table(rows, g, i_begin, i_count, sx, scale);
+    build_row_table(rows, nullptr, g, i_begin, i_count, sx, scale);
     float *pv = gproj + (int64_t)p * g.proj_view_stride;
     const int64_t proj_batch = (int64_t)g.P * g.proj_view_stride;
     const int plane = g.w * g.h;
     for (int k = threadIdx.x; k < g.h; k += blockDim.x) {
-        const AxisTap tv = axis_tap((float)k - g.half_h, sz, scale, g.phf, g.hph);
+        const AxisTap tv = axis_tap((float)k - g.half_h, sz, scale, g.div_ph, g.hph);
         const float wq = tv.w1, e = sub_rn(1.0f, wq);
         const bool c0 = (unsigned)tv.i0 < (unsigned)g.ph, c1 = (unsigned)(tv.i0 + 1) < (unsigned)g.ph;
         const float *o = gout + (int64_t)p * g.out_chan_stride + ((int64_t)i_begin * g.w + j) * g.h + k;
@@ -225,10 +250,10 @@ __global__ void __launch_bounds__(256) backproj_grid_kernel(float *__restrict__ 
     const float scale = view_scale(sy, g.w, j);
     const int64_t nv = (int64_t)g.d * g.w * g.h;
     const float xi = (float)(g.i_off + i) - g.half_d;
-    const float gu = mul_rn(div_rn(add_rn(mul_rn(sub_rn(xi, sx), scale), sx), g.pwf), 2.0f);
+    const float gu = mul_rn(div_const(add_rn(mul_rn(sub_rn(xi, sx), scale), sx), g.div_pw), 2.0f);
     for (int k = threadIdx.x; k < g.h; k += blockDim.x) {
         const float zk = (float)k - g.half_h;
-        const float gv = mul_rn(div_rn(add_rn(mul_rn(sub_rn(zk, sz), scale), sz), g.phf), 2.0f);
+        const float gv = mul_rn(div_const(add_rn(mul_rn(sub_rn(zk, sz), scale), sz), g.div_ph), 2.0f);
         const int64_t vox = ((int64_t)i * g.w + j) * g.h + k;
         grid[((int64_t)p * 2 + 0) * nv + vox] = gv;
         grid[((int64_t)p * 2 + 1) * nv + vox] = gu;
@@ -243,13 +268,13 @@ static int fill_dims(BpDims &g, int B, int P, int pw, int ph, int d_total, int w
     LR_REQUIRE(i_begin >= 0 && d > 0 && i_begin + d <= d_total, "backproject: slab [%d, %d) is not inside [0, %d)", i_begin,
                i_begin + d, d_total);
     LR_REQUIRE(d <= 65535 * (BP_ICHUNK / 2) && w < (1 << 30), "backproject: volume too large for the launch grid");
-    LR_REQUIRE((int64_t)(pw + 4) * ph < (1ll << 31) && (int64_t)w * h < (1ll << 31), "backproject: detector / plane too large for 32-bit offsets");
+    LR_REQUIRE((int64_t)(pw + 4) * ph < (1ll << 26) && (int64_t)w * h < (1ll << 31), "backproject: detector (pw*ph must be < 2^26) / plane too large for 32-bit offsets");
     g.B = B; g.P = P; g.pw = pw; g.ph = ph; g.d = d; g.w = w; g.h = h; g.p0 = 0; g.i_off = i_begin;
     const int n_chunks = (d + BP_ICHUNK - 1) / BP_ICHUNK;
     g.ichunk = (((d + n_chunks - 1) / n_chunks + 3) / 4) * 4;      // balanced, multiple of the unroll factor
     if (g.ichunk > BP_ICHUNK) g.ichunk = BP_ICHUNK;
     g.half_d = (float)((double)d_total / 2.0); g.half_h = (float)((double)h / 2.0);
-    g.pwf = (float)pw; g.phf = (float)ph;
+    g.div_pw = make_const_div((float)pw); g.div_ph = make_const_div((float)ph);
     g.hpw = (float)(pw - 1) / 2.0f; g.hph = (float)(ph - 1) / 2.0f;
     g.proj_view_stride = (int64_t)pw * ph;
     g.out_batch_stride = obs; g.out_chan_stride = ocs;
