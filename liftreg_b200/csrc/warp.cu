@@ -379,7 +379,7 @@ __device__ __forceinline__ void warp_bwd_phi_one(const float *__restrict__ gout_
 }
 
 template <bool SCALE, bool IDENT>
-__global__ void __launch_bounds__(WARP_TX * WARP_TY)
+__global__ void __launch_bounds__(WARP_TX * WARP_TY, 4)   // 64 registers: measured 45.0 us vs 47.4 us unconstrained (76 regs)
     warp_backward_phi_kernel(const float *__restrict__ gout, const float *__restrict__ img, const float *__restrict__ phi,
                              float *__restrict__ gphi, WarpDims g) {
     __shared__ IdentTable<WARP_TY * WARP_VY> ident;
