@@ -374,10 +374,12 @@ def run_b200(args):
     pool = ThreadPoolExecutor(2)
 
     def e2e_bp():
+        torch.cuda.set_device(local)      # the current device is per host thread; pool threads start on device 0
         _native.check(lib.lr_backproject_forward_host(vp(h_proj), pp, 1, P, DET[0], DET[1], VOL[0], VOL[1], VOL[2],
                                                       vp(h_lifted), vp(ws_bp), ws_bp.numel(), st), "backproject host")
 
     def e2e_warp():
+        torch.cuda.set_device(local)
         _native.check(lib.lr_warp_forward_host(vp(h_moving), vp(h_phi), 1, 1, VOL[0], VOL[1], VOL[2], 0, 0, 1, 0,
                                                vp(h_warped), vp(ws_w), ws_w.numel(), st2), "warp host")
 

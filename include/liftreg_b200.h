@@ -19,11 +19,15 @@
  *     device memory and keeps no state (geometry is passed by value per call).
  *   - all tensors are dense, C-contiguous fp32 unless a stride is given.
  *   - functions without the _host suffix take DEVICE pointers, are asynchronous
- *     on `stream` (a cudaStream_t) and never synchronise.
+ *     on `stream` (a cudaStream_t) and never synchronise.  As with any CUDA
+ *     launch, the calling thread's current device must be the device that owns
+ *     `stream` and the buffers (the current device is per host thread).
  *   - _host functions take HOST pointers (pinned for full speed) plus a device
  *     workspace of lr_*_workspace_bytes(); they enqueue H2D, kernels and D2H on
  *     `stream` and synchronise it before returning, like the reference calls
- *     they replace (which end in .cpu().numpy()).
+ *     they replace (which end in .cpu().numpy()).  When the host buffers are
+ *     pinned+mapped, lr_warp_forward_host lets the kernel stream the map and the
+ *     result over PCIe itself (set LIFTREG_B200_ZERO_COPY=0 to force staging).
  *   - return 0 on success, a negative lr_status on failure; never throws or
  *     exits.  lr_last_error() returns a thread-local message.
  *   - volume axes (d,w,h) = (axial, coronal, sagittal); detector (rd,rh);
