@@ -343,6 +343,17 @@ def run_b200(args):
                 "compulsory_bytes": comp_bytes, "gbps_compulsory": comp_bytes / us * 1e-3,
                 "gather_model_gbps": 16.0 * nominal / us * 1e-3}
 
+    # ---- DRR end to end: calculate_projection's numpy-in / numpy-out contract (sdct:59-100) as preprocessingDRR.py
+    # calls it (H2D of the 160^3 volume, kernel, D2H of the 4 x 240^2 images, synchronous), per call
+    drr_e2e_ms = None
+    if rank == 0:
+        for _ in range(2):
+            sdct.calculate_projection(mu, poses, (240, 240), [1, 1, 1], (2.2, 2.2, 2.2), dev)
+        t0 = time.perf_counter()
+        for _ in range(10):
+            sdct.calculate_projection(mu, poses, (240, 240), [1, 1, 1], (2.2, 2.2, 2.2), dev)
+        drr_e2e_ms = 1e2 * (time.perf_counter() - t0)
+
     # ---- e2e through the host-buffer C-ABI (pinned host memory, H2D + kernels + D2H every step)
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     h_proj, h_moving, h_phi = pin(target_proj), pin(moving), pin(phi)
@@ -450,6 +461,7 @@ def run_b200(args):
                          "algorithmic_bytes_per_launch": kern[dom]["bytes"], "us_per_launch": kern[dom]["us"]},
             "kernels": kern,
             "drr_forward_cfg1": {k: dict(v, frac_of_hbm_peak_compulsory=v["gbps_compulsory"] / peak) for k, v in drr_extra.items()},
+            "drr_calculate_projection_e2e_ms": drr_e2e_ms,
             "sustained_ms_per_step": sustained_ms,
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": world * units / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,

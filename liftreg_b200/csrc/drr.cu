@@ -176,7 +176,10 @@ __device__ __forceinline__ float finish_ray(float acc, const Ray &r, const DrrDi
 // marched by different warps; the run sums are combined in run order.  The summation order is therefore
 //     sum_{s} ( sum_{j in run s} sample_j ),  both levels ascending, fp32
 // which the oracle reproduces (seg_len argument); the reference's own order is torch.sum's vectorised cascade.
-__global__ void __launch_bounds__(32 * DRR_PAIRS * DRR_SEGS)
+#ifndef LR_DRR_MINB
+#define LR_DRR_MINB 4
+#endif
+__global__ void __launch_bounds__(32 * DRR_PAIRS * DRR_SEGS, LR_DRR_MINB)
     drr_forward_kernel(const float *__restrict__ vol, float *__restrict__ proj, DrrDims g, DrrViews views) {
     __shared__ float2 part[DRR_SEGS][DRR_PAIRS][32];
     const int v = blockIdx.x * 32 + threadIdx.x;
