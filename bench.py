@@ -353,6 +353,29 @@ def run_b200(args):
                 "compulsory_bytes": comp_bytes, "gbps_compulsory": comp_bytes / us * 1e-3,
                 "gather_model_gbps": 16.0 * nominal / us * 1e-3}
 
+    # ---- PCA-subspace decode (model :102): streams the 2.75 GB basis once
+    pca_extra = None
+    if rank == 0:
+        K = 56
+        basis = torch.empty((3 * nv, K), device=dev).normal_(0, 1e-3)
+        pmean = torch.zeros(3 * nv, device=dev)
+        coefs = torch.randn(1, K, device=dev)
+        pouts = [torch.empty((1, 3 * nv), device=dev) for _ in range(2)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            stx = ctypes.c_void_p(stream.cuda_stream)
+            for i in range(3):
+                _native.check(lib.lr_pca_decode(vp(coefs), vp(basis), vp(pmean), 1, K, 3 * nv, 1, VOL[0], VOL[1], VOL[2], vp(pouts[i % 2]), stx), "lr_pca_decode")
+            e0.record(stream)
+            for i in range(20):
+                _native.check(lib.lr_pca_decode(vp(coefs), vp(basis), vp(pmean), 1, K, 3 * nv, 1, VOL[0], VOL[1], VOL[2], vp(pouts[i % 2]), stx), "lr_pca_decode")
+            e1.record(stream)
+        torch.cuda.synchronize()
+        us = 1e3 * e0.elapsed_time(e1) / 20
+        pbytes = 4 * 3 * nv * K + 8 * 3 * nv
+        pca_extra = {"us": us, "bytes": pbytes, "gbps": pbytes / us * 1e-3, "workload": "B=1, K=56, N=3*160^3 (+mean, +identity)"}
+        del basis, pmean, pouts
+
     # ---- DRR end to end: calculate_projection's numpy-in / numpy-out contract (sdct:59-100) as preprocessingDRR.py
     # calls it (H2D of the 160^3 volume, kernel, D2H of the 4 x 240^2 images, synchronous), per call
     drr_e2e_ms = None
@@ -473,6 +496,7 @@ def run_b200(args):
             "kernels": kern,
             "drr_forward_cfg1": {k: dict(v, frac_of_hbm_peak_compulsory=v["gbps_compulsory"] / peak) for k, v in drr_extra.items()},
             "drr_calculate_projection_e2e_ms": drr_e2e_ms,
+            "pca_decode": dict(pca_extra, frac_of_hbm_peak=pca_extra["gbps"] / peak) if pca_extra else None,
             "sustained_ms_per_step": sustained_ms,
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": world * units / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,

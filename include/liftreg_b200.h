@@ -178,6 +178,18 @@ LR_API int lr_warp_forward_host(const float *img_host, const float *phi_host, in
                                 int padding, int mode, int using_scale, int disp_plus_identity, float *out_host,
                                 void *workspace, size_t workspace_bytes, lr_stream_t stream);
 
+/* ---- PCA-subspace displacement decode ------------- */
+/* replaces models/LiftRegDeformSubspaceBackproj.py:102
+ *     disp_field = F.linear(x, self.pca_vectors, self.pca_mean)          (x: (B,K) coefficients)
+ * and, if add_identity != 0, the `disp_field + self.id_transform` of :68 (N must then be 3*D*H*W; the (B,N) result
+ * reshaped to (B,3,D,H,W) is the map phi that lr_warp_forward consumes).
+ *   coefs (B,K); basis (N,K) row-major = pca_vectors as the model stores it (:42, 16-byte aligned, K % 4 == 0);
+ *   mean (N) nullable; out (B,N).
+ * out[b,n] = (sum_k coefs[b,k]*basis[n,k], fp32 FMA chain, k ascending) + mean[n] (+ identity(n)).
+ * The 4*N*K-byte basis (2.75 GB at 160^3, K = 56) is streamed from HBM exactly once for up to 32 batch items. */
+LR_API int lr_pca_decode(const float *coefs, const float *basis, const float *mean, int B, int K, int64_t N,
+                         int add_identity, int D, int H, int W, float *out, lr_stream_t stream);
+
 /* ---- HU -> attenuation -------------------------------------------------- */
 /* replaces sdct:6-13 calc_relative_atten_coef(_cuda): mu = (max(HU,-1000)+1000)/1000*0.2; in place allowed */
 LR_API int lr_atten_coef(const float *hu, int64_t n, float *mu, lr_stream_t stream);

@@ -1,0 +1,185 @@
+// PCA-subspace displacement decode: disp = coefs @ basis^T + mean (+ identity map), sm_100a.
+//
+// Replaces reference src/liftreg/models/LiftRegDeformSubspaceBackproj.py:102
+//     disp_field = F.linear(x, self.pca_vectors, self.pca_mean).reshape(B, 3, D, W, H)
+// and, optionally, the `+ self.id_transform` of :68.  pca_vectors is (N, K) row-major with
+// N = 3*D*W*H = 12.3 M and K = 56 at 160^3: a 2.75 GB basis streamed once per forward -- by far the largest HBM
+// consumer of the model's forward pass and purely bandwidth-bound (algorithmic bytes = 4*N*K + 4*N + 4*B*(N + K)).
+//
+// Layout: a block owns tiles of 256 consecutive basis rows (256*K contiguous floats).  The tile is copied with
+// perfectly coalesced 16-byte streaming loads into shared memory (STS.128) with a row pitch whose quarter is odd, so
+// that in the compute phase lane = row reads its row four coefficients at a time (LDS.128) without bank conflicts; the
+// batch's coefficients sit in shared memory as [k][b] and are read four batch items at a time (LDS.128 broadcast).
+// Accumulation is a sequential fp32 FMA chain over k (ascending), then + mean, then (optionally) + identity -- the
+// order the oracle restates.
+#include "common.cuh"
+
+namespace lr {
+
+#ifndef LR_PD_ROWS
+#define LR_PD_ROWS 256
+#endif
+constexpr int PD_ROWS = LR_PD_ROWS;     // basis rows per tile = threads per block
+// shared-memory row pitch in floats: a multiple of 4 (aligned STS.128 / LDS.128) whose quarter is odd (8 consecutive
+// lanes x 16 B then cover all 32 banks exactly once)
+__host__ __device__ inline int pd_pitch(int K) { return (K / 4) % 2 == 0 ? K + 4 : K + 8; }
+
+struct PcaDims {
+    int B, K;
+    int64_t N;                   // rows of the basis = 3*D*H*W when add_identity
+    int add_identity;
+    int D, H, W, nvox;           // identity map geometry (axis c of output row n = n / nvox)
+    double sp0, sp1, sp2;        // 1/(D-1), 1/(H-1), 1/(W-1) in float64 (net_utils.py:81)
+    int64_t n_tiles;
+};
+
+// net_utils.py:81-85 with numpy>=2 casting (same helper as warp.cu)
+__device__ __forceinline__ float pd_identity_coord(int idx, double spacing) {
+    float v = __double2float_rn((double)idx * spacing);
+    return sub_rn(mul_rn(v, 2.0f), 1.0f);
+}
+
+template <int BT>   // batch items held in registers per pass (B <= BT)
+__global__ void __launch_bounds__(PD_ROWS)
+    pca_decode_kernel(const float *__restrict__ coefs, const float *__restrict__ basis, const float *__restrict__ mean,
+                      float *__restrict__ out, PcaDims g) {
+    extern __shared__ float smem[];
+    const int pitch = pd_pitch(g.K);
+    float *tile = smem;                                  // [PD_ROWS][pitch]
+    float *cf = smem + (size_t)PD_ROWS * pitch;          // [K][BT], zero-padded beyond B
+    const int tid = threadIdx.x;
+    for (int i = tid; i < g.K * BT; i += PD_ROWS) {
+        const int k = i / BT, b = i - k * BT;
+        cf[i] = b < g.B ? coefs[(int64_t)b * g.K + k] : 0.0f;
+    }
+    const int k4 = g.K / 4;                              // float4 per row (K % 4 == 0 on this path)
+    const int tile_f4 = PD_ROWS * k4;
+
+    for (int64_t t = blockIdx.x; t < g.n_tiles; t += gridDim.x) {
+        const int64_t row0 = t * PD_ROWS;
+        const int rows = (int)min((int64_t)PD_ROWS, g.N - row0);
+        __syncthreads();                                 // previous tile fully consumed (and cf written)
+        // ---- stage: rows*K contiguous floats, coalesced 16 B streaming loads, transposed into shared memory
+        const float4 *src = reinterpret_cast<const float4 *>(basis + row0 * g.K);
+        const int n_f4 = rows * k4;
+#ifndef LR_PD_UNR
+#define LR_PD_UNR 7
+#endif
+        constexpr int UNR = LR_PD_UNR;                           // loads in flight per thread before the first store
+        for (int f0 = tid; f0 < tile_f4; f0 += UNR * PD_ROWS) {
+            float4 v[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int f = f0 + u * PD_ROWS;
+                if (f < n_f4) v[u] = ld_stream4(src + f);
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int f = f0 + u * PD_ROWS;
+                if (f < n_f4) {
+                    const int r = f / k4, k = (f - r * k4) * 4;
+                    *reinterpret_cast<float4 *>(tile + r * pitch + k) = v[u];
+                }
+            }
+        }
+        __syncthreads();
+        if (tid < rows) {
+            float acc[BT];
+#pragma unroll
+            for (int b = 0; b < BT; ++b) acc[b] = 0.0f;
+            const float *myrow = tile + tid * pitch;
+            for (int k = 0; k < g.K; k += 4) {
+                const float4 w4 = *reinterpret_cast<const float4 *>(myrow + k);
+                const float w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {          // k ascending: one sequential fp32 FMA chain per output
+                    if (BT >= 4) {
+#pragma unroll
+                        for (int b = 0; b < BT; b += 4) {
+                            const float4 c = *reinterpret_cast<const float4 *>(cf + (k + kk) * BT + b);
+                            acc[b] = fma_rn(c.x, w[kk], acc[b]); acc[b + 1] = fma_rn(c.y, w[kk], acc[b + 1]);
+                            acc[b + 2] = fma_rn(c.z, w[kk], acc[b + 2]); acc[b + 3] = fma_rn(c.w, w[kk], acc[b + 3]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int b = 0; b < BT; ++b) acc[b] = fma_rn(cf[(k + kk) * BT + b], w[kk], acc[b]);
+                    }
+                }
+            }
+            const int64_t n = row0 + tid;
+            const float m = mean ? ld_stream(mean + n) : 0.0f;
+            float idv = 0.0f;
+            if (g.add_identity) {                         // model :68: deform_field = disp_field + id_transform
+                const int c = (int)(n / g.nvox);
+                const int v = (int)(n - (int64_t)c * g.nvox);
+                const int z = v / (g.H * g.W), rem = v - z * (g.H * g.W), y = rem / g.W, x = rem - y * g.W;
+                idv = c == 0 ? pd_identity_coord(z, g.sp0) : (c == 1 ? pd_identity_coord(y, g.sp1) : pd_identity_coord(x, g.sp2));
+            }
+#pragma unroll
+            for (int b = 0; b < BT; ++b) {
+                if (b < g.B) {
+                    float o = add_rn(acc[b], m);
+                    if (g.add_identity) o = add_rn(o, idv);
+                    st_stream(out + (int64_t)b * g.N + n, o);
+                }
+            }
+        }
+    }
+}
+
+template <int BT>
+static int launch_pca(const float *coefs, const float *basis, const float *mean, float *out, const PcaDims &g,
+                      cudaStream_t st) {
+    const size_t smem = sizeof(float) * ((size_t)PD_ROWS * pd_pitch(g.K) + (size_t)g.K * BT);
+    static bool attr_set = false;       // raising the dynamic shared memory limit is idempotent per function
+    if (smem > 48 * 1024 && !attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(pca_decode_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) { set_error("pca_decode: cannot raise shared memory limit: %s", cudaGetErrorString(e)); return LR_ERR_CUDA; }
+        attr_set = true;
+    }
+    int blocks_per_sm = (int)((220 * 1024) / (smem + 1024));
+    if (blocks_per_sm > 12) blocks_per_sm = 12;
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
+    int64_t grid = (int64_t)148 * blocks_per_sm;
+    if (grid > g.n_tiles) grid = g.n_tiles;
+    pca_decode_kernel<BT><<<(unsigned)grid, PD_ROWS, smem, st>>>(coefs, basis, mean, out, g);
+    return check_launch("pca_decode_kernel");
+}
+
+}  // namespace lr
+
+using namespace lr;
+
+extern "C" int lr_pca_decode(const float *coefs, const float *basis, const float *mean, int B, int K, int64_t N,
+                             int add_identity, int D, int H, int W, float *out, lr_stream_t stream) {
+    LR_REQUIRE(coefs && basis && out, "pca_decode: null pointer");
+    LR_REQUIRE(B > 0 && K > 0 && N > 0, "pca_decode: non-positive dimension (B=%d K=%d N=%lld)", B, K, (long long)N);
+    LR_REQUIRE(K % 4 == 0 && K <= 256, "pca_decode: K must be a multiple of 4 and <= 256 (got %d)", K);
+    LR_REQUIRE(((uintptr_t)basis & 15) == 0, "pca_decode: basis must be 16-byte aligned");
+    if (add_identity) {
+        LR_REQUIRE(D > 1 && H > 1 && W > 1 && (int64_t)3 * D * H * W == N && (int64_t)D * H * W < (1ll << 31),
+                   "pca_decode: add_identity needs N == 3*D*H*W (N=%lld, D=%d H=%d W=%d)", (long long)N, D, H, W);
+    }
+    PcaDims g;
+    g.K = K; g.N = N; g.add_identity = add_identity != 0;
+    g.D = D; g.H = H; g.W = W; g.nvox = add_identity ? D * H * W : 1;
+    g.sp0 = D > 1 ? 1.0 / (double)(D - 1) : 0.0; g.sp1 = H > 1 ? 1.0 / (double)(H - 1) : 0.0; g.sp2 = W > 1 ? 1.0 / (double)(W - 1) : 0.0;
+    g.n_tiles = (N + PD_ROWS - 1) / PD_ROWS;
+    cudaStream_t st = as_stream(stream);
+    // batch items beyond 32 take further passes over the basis
+    for (int b0 = 0; b0 < B; b0 += 32) {
+        const int nb = B - b0 < 32 ? B - b0 : 32;
+        g.B = nb;
+        const float *c = coefs + (int64_t)b0 * K;
+        float *o = out + (int64_t)b0 * N;
+        int e;
+        if (nb <= 1) e = launch_pca<1>(c, basis, mean, o, g, st);
+        else if (nb <= 2) e = launch_pca<2>(c, basis, mean, o, g, st);
+        else if (nb <= 4) e = launch_pca<4>(c, basis, mean, o, g, st);
+        else if (nb <= 8) e = launch_pca<8>(c, basis, mean, o, g, st);
+        else if (nb <= 16) e = launch_pca<16>(c, basis, mean, o, g, st);
+        else e = launch_pca<32>(c, basis, mean, o, g, st);
+        if (e) return e;
+    }
+    return LR_OK;
+}

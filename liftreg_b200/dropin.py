@@ -34,9 +34,9 @@ def _estimate_flow(self, moving, target_proj, poses):
 
     Lines 85-98 (cached backprojection grid, F.grid_sample, .detach(), torch.cat with `moving`) become one kernel
     that writes channels 1..P of the encoder input; channel 0 is a copy of `moving`.  Geometry comes from batch item
-    0 like the reference (:85-87).  Lines 99-104 (encoder, FC, PCA decode) are the reference's own modules."""
+    0 like the reference (:85-87).  Lines 99-100 (encoder, FC) are the reference's own modules; the PCA decode of :102
+    is the streaming lr_pca_decode kernel."""
     import torch
-    import torch.nn.functional as F
     B, _, D, W, H = moving.shape
     P = target_proj.shape[1]
     x = torch.empty((B, 1 + P, D, W, H), device=moving.device, dtype=moving.dtype)
@@ -45,7 +45,8 @@ def _estimate_flow(self, moving, target_proj, poses):
         _ops.backproject(target_proj.detach(), poses[0:1].detach().cpu().numpy(), (D, W, H), out=x, channel_offset=1)
     for enc in self.encoders:
         x = enc(x)
-    disp_field = F.linear(x, self.pca_vectors, self.pca_mean).reshape(B, 3, D, W, H)
+    # :102  F.linear(x, pca_vectors, pca_mean): one streaming pass over the 2.75 GB basis (lr_pca_decode)
+    disp_field = _ops.pca_decode(x, self.pca_vectors, self.pca_mean, img_shape=(D, W, H))
     return x, disp_field
 
 

@@ -298,3 +298,46 @@ def atten_coef_(img):
     with torch.cuda.device(t.device):
         _native.check(_native.lib().lr_atten_coef(_ptr(t), t.numel(), _ptr(t), _stream()), "lr_atten_coef")
     return img
+
+
+# --------------------------------------------------------------------------- PCA-subspace decode (row f2)
+class _PcaDecode(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, coefs, basis, mean, D, H, W, add_identity):
+        coefs = _need_cuda_f32(coefs, "coefs")
+        basis = _need_cuda_f32(basis, "pca_vectors")
+        mean_c = _need_cuda_f32(mean, "pca_mean") if mean is not None else None
+        B, K = coefs.shape
+        N = basis.shape[0]
+        out = torch.empty((B, N), device=coefs.device, dtype=torch.float32)
+        with torch.cuda.device(coefs.device):
+            _native.check(_native.lib().lr_pca_decode(_ptr(coefs), _ptr(basis), _ptr(mean_c), B, K, N, int(add_identity),
+                                                      D, H, W, _ptr(out), _stream()), "lr_pca_decode")
+        ctx.save_for_backward(basis)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (basis,) = ctx.saved_tensors
+        # d/dcoefs = grad_out (B,N) @ basis (N,K): a library GEMM; the basis and the mean are frozen buffers in the model
+        return grad_out @ basis, None, None, None, None, None, None
+
+
+def pca_decode(coefs, pca_vectors, pca_mean=None, img_shape=None, add_identity=False):
+    """disp = F.linear(coefs, pca_vectors, pca_mean) as one streaming kernel (reference model :102); with
+    add_identity (needs img_shape = (D,H,W), N = 3*D*H*W) the identity map of model :68 is added too, so the result
+    reshaped to (B,3,D,H,W) is the map the warp consumes.  coefs (B,K); pca_vectors (N,K) as the model stores it
+    (:42); pca_mean (N).  Differentiable wrt coefs."""
+    if coefs.dim() != 2 or pca_vectors.dim() != 2 or coefs.shape[1] != pca_vectors.shape[1]:
+        raise ValueError("expected coefs (B,K) and pca_vectors (N,K); got %s and %s" % (tuple(coefs.shape), tuple(pca_vectors.shape)))
+    if pca_mean is not None and tuple(pca_mean.shape) != (pca_vectors.shape[0],):
+        raise ValueError("pca_mean must be (N,)")
+    D = H = W = 0
+    if add_identity:
+        if img_shape is None or 3 * int(np.prod(img_shape)) != pca_vectors.shape[0]:
+            raise ValueError("add_identity needs img_shape with 3*D*H*W == N")
+        D, H, W = (int(s) for s in img_shape)
+    out = _PcaDecode.apply(coefs, pca_vectors, pca_mean, D, H, W, bool(add_identity))
+    if img_shape is not None:
+        return out.reshape(coefs.shape[0], 3, *[int(s) for s in img_shape])
+    return out

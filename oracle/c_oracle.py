@@ -173,3 +173,15 @@ def atten_coef(hu):
     mu = np.empty_like(hu)
     lib().lro_atten_coef(_p(hu), ctypes.c_int64(hu.size), _p(mu))
     return mu
+
+
+def pca_decode(coefs, basis, mean=None, img_shape=None):
+    """LiftRegDeformSubspaceBackproj.py:102 (+ :68 when img_shape is given): (B,K),(N,K),(N) -> (B,N)."""
+    coefs = _f32(coefs); basis = _f32(basis)
+    B, K = coefs.shape
+    N = basis.shape[0]
+    mean = _f32(mean) if mean is not None else None
+    D, H, W = (int(s) for s in img_shape) if img_shape is not None else (0, 0, 0)
+    out = np.empty((B, N), np.float32)
+    lib().lro_pca_decode(_p(coefs), _p(basis), _p(mean), B, K, ctypes.c_int64(N), int(img_shape is not None), D, H, W, _p(out))
+    return out

@@ -470,4 +470,32 @@ LRO_API void lro_atten_coef(const float *hu, int64_t n, float *mu) {
     }
 }
 
+/* models/LiftRegDeformSubspaceBackproj.py:102 (+ :68 if add_identity):
+ *   out[b,n] = (sum_k coefs[b,k]*basis[n,k]) + mean[n] (+ identity_map(n)),  fp32, one fmaf chain over k ascending.
+ * F.linear's own accumulation order is cuBLAS / MKL internal; any order agrees with this one to ~1e-7 relative. */
+LRO_API void lro_pca_decode(const float *coefs, const float *basis, const float *mean, int B, int K, int64_t N,
+                            int add_identity, int D, int H, int W, float *out) {
+    int sz[3] = {D, H, W};
+    int64_t nvox = (int64_t)D * H * W;
+#pragma omp parallel for schedule(static)
+    for (int64_t n = 0; n < N; ++n) {
+        float idv = 0.0f;
+        if (add_identity) {
+            int c = (int)(n / nvox);
+            int64_t v = n - (int64_t)c * nvox;
+            int z = (int)(v / ((int64_t)H * W)), y = (int)((v / W) % H), x = (int)(v % W);
+            int idx = c == 0 ? z : (c == 1 ? y : x);
+            float t = (float)((double)idx * (1.0 / (double)(sz[c] - 1)));
+            idv = t * 2.0f - 1.0f;
+        }
+        for (int b = 0; b < B; ++b) {
+            float acc = 0.0f;
+            for (int k = 0; k < K; ++k) acc = fmaf(coefs[(size_t)b * K + k], basis[(size_t)n * K + k], acc);
+            float o = acc + (mean ? mean[n] : 0.0f);
+            if (add_identity) o = o + idv;
+            out[(size_t)b * N + n] = o;
+        }
+    }
+}
+
 LRO_API int lro_version(void) { return 1; }

@@ -589,3 +589,40 @@ def test_remaining_mirror_entry_points(dev):
         assert per_image_rel_l2(o, d1["proj"]) <= TOL
     d2 = load_golden("drr_small_csvposes")
     assert per_image_rel_l2(pr.project_numpy(d2["vol"], d2["poses"], d2["resolution"], d2["spacing"]), d2["proj"]) <= TOL
+
+
+# ------------------------------------------------------------------ PCA-subspace decode (row f2)
+@pytest.mark.parametrize("B,K,shape", [(1, 56, (6, 5, 7)), (3, 56, (20, 24, 28)), (8, 8, (4, 4, 4)), (33, 60, (5, 6, 7)), (2, 4, (3, 3, 3))])
+def test_pca_decode_exact_vs_oracle(dev, B, K, shape):
+    from liftreg_b200 import ops
+    from oracle import c_oracle
+    rs = np.random.RandomState(50)
+    N = 3 * int(np.prod(shape))
+    basis = (rs.standard_normal((N, K)) * 1e-2).astype(np.float32)
+    mean = (rs.standard_normal(N) * 1e-2).astype(np.float32)
+    coefs = rs.standard_normal((B, K)).astype(np.float32)
+    out = ops.pca_decode(cu(coefs, dev), cu(basis, dev), cu(mean, dev))
+    assert np.array_equal(out.cpu().numpy(), c_oracle.pca_decode(coefs, basis, mean))
+    phi = ops.pca_decode(cu(coefs, dev), cu(basis, dev), cu(mean, dev), img_shape=shape, add_identity=True)
+    assert phi.shape == (B, 3) + shape
+    assert np.array_equal(phi.reshape(B, -1).cpu().numpy(), c_oracle.pca_decode(coefs, basis, mean, img_shape=shape))
+    nomean = ops.pca_decode(cu(coefs, dev), cu(basis, dev))
+    assert np.array_equal(nomean.cpu().numpy(), c_oracle.pca_decode(coefs, basis))
+
+
+def test_pca_decode_matches_torch_linear_and_is_differentiable(dev):
+    import torch.nn.functional as F
+    from liftreg_b200 import net_utils, ops
+    rs = np.random.RandomState(51)
+    shape = (16, 12, 20)
+    N, K, B = 3 * int(np.prod(shape)), 56, 4
+    basis = cu((rs.standard_normal((N, K)) * 1e-2).astype(np.float32), dev)
+    mean = cu((rs.standard_normal(N) * 1e-2).astype(np.float32), dev)
+    c1 = cu(rs.standard_normal((B, K)).astype(np.float32), dev).requires_grad_(True)
+    c2 = c1.detach().clone().requires_grad_(True)
+    ref = F.linear(c1, basis, mean).reshape(B, 3, *shape) + net_utils.gen_identity_map(shape, 1.0)    # model :102, :68
+    ours = ops.pca_decode(c2, basis, mean, img_shape=shape, add_identity=True)
+    assert rel_l2(ours.detach().cpu().numpy(), ref.detach().cpu().numpy()) <= TOL
+    g = cu(rs.standard_normal(ref.shape).astype(np.float32), dev)
+    ref.backward(g); ours.backward(g)
+    assert rel_l2(c2.grad.cpu().numpy(), c1.grad.cpu().numpy()) <= GRAD_TOL
