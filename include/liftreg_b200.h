@@ -183,7 +183,8 @@ LR_API int lr_warp_forward_host(const float *img_host, const float *phi_host, in
  *     disp_field = F.linear(x, self.pca_vectors, self.pca_mean)          (x: (B,K) coefficients)
  * and, if add_identity != 0, the `disp_field + self.id_transform` of :68 (N must then be 3*D*H*W; the (B,N) result
  * reshaped to (B,3,D,H,W) is the map phi that lr_warp_forward consumes).
- *   coefs (B,K); basis (N,K) row-major = pca_vectors as the model stores it (:42, 16-byte aligned, K % 4 == 0);
+ *   coefs (B,K); basis (N,K) row-major = pca_vectors as the model stores it (:42); K <= 160; the fast path needs
+ *   K % 4 == 0 and a 16-byte aligned basis (anything else takes a scalar staging path);
  *   mean (N) nullable; out (B,N).
  * out[b,n] = (sum_k coefs[b,k]*basis[n,k], fp32 FMA chain, k ascending) + mean[n] (+ identity(n)).
  * The 4*N*K-byte basis (2.75 GB at 160^3, K = 56) is streamed from HBM exactly once for up to 32 batch items. */

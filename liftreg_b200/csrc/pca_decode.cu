@@ -39,6 +39,60 @@ __device__ __forceinline__ float pd_identity_coord(int idx, double spacing) {
     return sub_rn(mul_rn(v, 2.0f), 1.0f);
 }
 
+// Fallback for K % 4 != 0 or an unaligned basis: scalar staging with an odd row pitch (conflict-free scalar reads).
+template <int BT>
+__global__ void __launch_bounds__(PD_ROWS)
+    pca_decode_scalar_kernel(const float *__restrict__ coefs, const float *__restrict__ basis, const float *__restrict__ mean,
+                             float *__restrict__ out, PcaDims g) {
+    extern __shared__ float smem[];
+    const int pitch = g.K | 1;
+    float *tile = smem;
+    float *cf = smem + (size_t)PD_ROWS * pitch;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < g.K * BT; i += PD_ROWS) {
+        const int k = i / BT, b = i - k * BT;
+        cf[i] = b < g.B ? coefs[(int64_t)b * g.K + k] : 0.0f;
+    }
+    for (int64_t t = blockIdx.x; t < g.n_tiles; t += gridDim.x) {
+        const int64_t row0 = t * PD_ROWS;
+        const int rows = (int)min((int64_t)PD_ROWS, g.N - row0);
+        __syncthreads();
+        const float *src = basis + row0 * g.K;
+        for (int f = tid; f < rows * g.K; f += PD_ROWS) {
+            const int r = f / g.K;
+            tile[r * pitch + (f - r * g.K)] = ld_stream(src + f);
+        }
+        __syncthreads();
+        if (tid < rows) {
+            float acc[BT];
+#pragma unroll
+            for (int b = 0; b < BT; ++b) acc[b] = 0.0f;
+            for (int k = 0; k < g.K; ++k) {
+                const float w = tile[tid * pitch + k];
+#pragma unroll
+                for (int b = 0; b < BT; ++b) acc[b] = fma_rn(cf[k * BT + b], w, acc[b]);
+            }
+            const int64_t n = row0 + tid;
+            const float m = mean ? ld_stream(mean + n) : 0.0f;
+            float idv = 0.0f;
+            if (g.add_identity) {
+                const int c = (int)(n / g.nvox);
+                const int v = (int)(n - (int64_t)c * g.nvox);
+                const int z = v / (g.H * g.W), rem = v - z * (g.H * g.W), y = rem / g.W, x = rem - y * g.W;
+                idv = c == 0 ? pd_identity_coord(z, g.sp0) : (c == 1 ? pd_identity_coord(y, g.sp1) : pd_identity_coord(x, g.sp2));
+            }
+#pragma unroll
+            for (int b = 0; b < BT; ++b) {
+                if (b < g.B) {
+                    float o = add_rn(acc[b], m);
+                    if (g.add_identity) o = add_rn(o, idv);
+                    st_stream(out + (int64_t)b * g.N + n, o);
+                }
+            }
+        }
+    }
+}
+
 template <int BT>   // batch items held in registers per pass (B <= BT)
 __global__ void __launch_bounds__(PD_ROWS)
     pca_decode_kernel(const float *__restrict__ coefs, const float *__restrict__ basis, const float *__restrict__ mean,
@@ -130,19 +184,22 @@ __global__ void __launch_bounds__(PD_ROWS)
 template <int BT>
 static int launch_pca(const float *coefs, const float *basis, const float *mean, float *out, const PcaDims &g,
                       cudaStream_t st) {
-    const size_t smem = sizeof(float) * ((size_t)PD_ROWS * pd_pitch(g.K) + (size_t)g.K * BT);
-    static bool attr_set = false;       // raising the dynamic shared memory limit is idempotent per function
-    if (smem > 48 * 1024 && !attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(pca_decode_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    const bool vec = g.K % 4 == 0 && ((uintptr_t)basis & 15) == 0;
+    const int pitch = vec ? pd_pitch(g.K) : (g.K | 1);
+    const size_t smem = sizeof(float) * ((size_t)PD_ROWS * pitch + (size_t)g.K * BT);
+    if (smem > 200 * 1024) { set_error("pca_decode: K=%d needs %zu bytes of shared memory", g.K, smem); return LR_ERR_BAD_ARGUMENT; }
+    if (smem > 48 * 1024) {       // opt in to large dynamic shared memory (idempotent, cheap)
+        cudaError_t e = vec ? cudaFuncSetAttribute(pca_decode_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)
+                            : cudaFuncSetAttribute(pca_decode_scalar_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) { set_error("pca_decode: cannot raise shared memory limit: %s", cudaGetErrorString(e)); return LR_ERR_CUDA; }
-        attr_set = true;
     }
     int blocks_per_sm = (int)((220 * 1024) / (smem + 1024));
-    if (blocks_per_sm > 12) blocks_per_sm = 12;
+    if (blocks_per_sm > 8) blocks_per_sm = 8;
     if (blocks_per_sm < 1) blocks_per_sm = 1;
     int64_t grid = (int64_t)148 * blocks_per_sm;
     if (grid > g.n_tiles) grid = g.n_tiles;
-    pca_decode_kernel<BT><<<(unsigned)grid, PD_ROWS, smem, st>>>(coefs, basis, mean, out, g);
+    if (vec) pca_decode_kernel<BT><<<(unsigned)grid, PD_ROWS, smem, st>>>(coefs, basis, mean, out, g);
+    else pca_decode_scalar_kernel<BT><<<(unsigned)grid, PD_ROWS, smem, st>>>(coefs, basis, mean, out, g);
     return check_launch("pca_decode_kernel");
 }
 
@@ -154,8 +211,7 @@ extern "C" int lr_pca_decode(const float *coefs, const float *basis, const float
                              int add_identity, int D, int H, int W, float *out, lr_stream_t stream) {
     LR_REQUIRE(coefs && basis && out, "pca_decode: null pointer");
     LR_REQUIRE(B > 0 && K > 0 && N > 0, "pca_decode: non-positive dimension (B=%d K=%d N=%lld)", B, K, (long long)N);
-    LR_REQUIRE(K % 4 == 0 && K <= 256, "pca_decode: K must be a multiple of 4 and <= 256 (got %d)", K);
-    LR_REQUIRE(((uintptr_t)basis & 15) == 0, "pca_decode: basis must be 16-byte aligned");
+    LR_REQUIRE(K <= 160, "pca_decode: K must be <= 160 (got %d)", K);
     if (add_identity) {
         LR_REQUIRE(D > 1 && H > 1 && W > 1 && (int64_t)3 * D * H * W == N && (int64_t)D * H * W < (1ll << 31),
                    "pca_decode: add_identity needs N == 3*D*H*W (N=%lld, D=%d H=%d W=%d)", (long long)N, D, H, W);

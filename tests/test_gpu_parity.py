@@ -592,7 +592,8 @@ def test_remaining_mirror_entry_points(dev):
 
 
 # ------------------------------------------------------------------ PCA-subspace decode (row f2)
-@pytest.mark.parametrize("B,K,shape", [(1, 56, (6, 5, 7)), (3, 56, (20, 24, 28)), (8, 8, (4, 4, 4)), (33, 60, (5, 6, 7)), (2, 4, (3, 3, 3))])
+@pytest.mark.parametrize("B,K,shape", [(1, 56, (6, 5, 7)), (3, 56, (20, 24, 28)), (8, 8, (4, 4, 4)), (33, 60, (5, 6, 7)), (2, 4, (3, 3, 3)),
+                                       (2, 3, (9, 8, 7)), (5, 57, (12, 10, 11)), (1, 1, (2, 2, 2))])
 def test_pca_decode_exact_vs_oracle(dev, B, K, shape):
     from liftreg_b200 import ops
     from oracle import c_oracle
