@@ -15,6 +15,21 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_sessionstart(session):
+    """Make sure the native library and the C oracle are built (no-ops when up to date; nvcc/gcc cross-compile on a
+    CPU-only box).  A failure here is reported by the tests that need the artefacts, not swallowed."""
+    try:
+        from liftreg_b200 import build as native_build
+        native_build.build()
+    except Exception as e:  # pragma: no cover
+        print("WARNING: could not build libliftreg_b200.so: %r" % (e,))
+    try:
+        from oracle import c_oracle
+        c_oracle.build()
+    except Exception as e:  # pragma: no cover
+        print("WARNING: could not build the C oracle: %r" % (e,))
+
+
 def load_golden(name):
     with np.load(os.path.join(GOLDEN, name + ".npz")) as z:
         return {k: z[k] for k in z.files}
