@@ -191,6 +191,11 @@ LR_API int lr_warp_forward_host(const float *img_host, const float *phi_host, in
 LR_API int lr_pca_decode(const float *coefs, const float *basis, const float *mean, int B, int K, int64_t N,
                          int add_identity, int D, int H, int W, float *out, lr_stream_t stream);
 
+/* adjoint wrt the coefficients (autograd of F.linear at model :102): grad_coefs (B,K) is ACCUMULATED into (caller
+ * zero-initialises): grad_coefs[b,k] += sum_n grad_out[b,n] * basis[n,k].  K % 4 == 0, basis 16-byte aligned. */
+LR_API int lr_pca_decode_backward(const float *grad_out, const float *basis, int B, int K, int64_t N,
+                                  float *grad_coefs, lr_stream_t stream);
+
 /* ---- HU -> attenuation -------------------------------------------------- */
 /* replaces sdct:6-13 calc_relative_atten_coef(_cuda): mu = (max(HU,-1000)+1000)/1000*0.2; in place allowed */
 LR_API int lr_atten_coef(const float *hu, int64_t n, float *mu, lr_stream_t stream);

@@ -39,6 +39,7 @@ SIGNATURES = {
     "lr_warp_forward_host_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "lr_warp_forward_host": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "lr_pca_decode": (_i, [_vp, _vp, _vp, _i, _i, _i64, _i, _i, _i, _i, _vp, _vp]),
+    "lr_pca_decode_backward": (_i, [_vp, _vp, _i, _i, _i64, _vp, _vp]),
     "lr_atten_coef": (_i, [_vp, _i64, _vp, _vp]),
 }
 

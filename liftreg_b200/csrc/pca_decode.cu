@@ -181,6 +181,85 @@ __global__ void __launch_bounds__(PD_ROWS)
     }
 }
 
+// Adjoint wrt the coefficients: grad_coefs[b,k] += sum_n grad_out[b,n] * basis[n,k] -- the second full pass over the
+// basis that a training step makes (autograd of F.linear at model :102).  Same tile staging as the forward; thread
+// (k, row-group) accumulates its column over a quarter of the tile's rows for all batch items, partial sums stay in
+// registers across the block's tiles and are reduced once at the end (shared memory, then RED.ADD.F32: the summation
+// order across blocks is not fixed, results agree with a sequential sum to fp32 round-off).
+template <int BT>
+__global__ void __launch_bounds__(PD_ROWS)
+    pca_decode_backward_kernel(const float *__restrict__ gout, const float *__restrict__ basis, float *__restrict__ gcoefs,
+                               PcaDims g) {
+    extern __shared__ float smem[];
+    const int pitch = pd_pitch(g.K);
+    float *tile = smem;                                  // [PD_ROWS][pitch]
+    float *gs = smem + (size_t)PD_ROWS * pitch;          // [PD_ROWS][BT] grad_out of the tile's rows
+    const int tid = threadIdx.x;
+    const int kpad = ((g.K + 31) / 32) * 32;             // threads per row-group (whole warps)
+    const int n_groups = PD_ROWS / kpad > 0 ? PD_ROWS / kpad : 1;
+    const int grp = tid / kpad, k = tid - grp * kpad;
+    const bool worker = grp < n_groups && k < g.K;
+    const int rows_per_grp = PD_ROWS / n_groups;
+    const int k4 = g.K / 4;
+    const int tile_f4 = PD_ROWS * k4;
+    float acc[BT];
+#pragma unroll
+    for (int b = 0; b < BT; ++b) acc[b] = 0.0f;
+
+    for (int64_t t = blockIdx.x; t < g.n_tiles; t += gridDim.x) {
+        const int64_t row0 = t * PD_ROWS;
+        const int rows = (int)min((int64_t)PD_ROWS, g.N - row0);
+        __syncthreads();
+        const float4 *src = reinterpret_cast<const float4 *>(basis + row0 * g.K);
+        const int n_f4 = rows * k4;
+        constexpr int UNR = 7;
+        for (int f0 = tid; f0 < tile_f4; f0 += UNR * PD_ROWS) {
+            float4 v[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int f = f0 + u * PD_ROWS;
+                if (f < n_f4) v[u] = ld_stream4(src + f);
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int f = f0 + u * PD_ROWS;
+                if (f < n_f4) {
+                    const int r = f / k4, kk = (f - r * k4) * 4;
+                    *reinterpret_cast<float4 *>(tile + r * pitch + kk) = v[u];
+                }
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < BT; ++b)                      // thread = row: its grad_out values (0 beyond the end)
+            gs[tid * BT + b] = (tid < rows && b < g.B) ? ld_stream(gout + (int64_t)b * g.N + row0 + tid) : 0.0f;
+        __syncthreads();
+        if (worker) {
+            const int r_lo = grp * rows_per_grp, r_hi = min(rows, r_lo + rows_per_grp);
+            for (int r = r_lo; r < r_hi; ++r) {
+                const float w = tile[r * pitch + k];
+#pragma unroll
+                for (int b = 0; b < BT; ++b) acc[b] = fmaf(gs[r * BT + b], w, acc[b]);
+            }
+        }
+    }
+    // block reduction over the row groups, then one RED per (b,k)
+    __syncthreads();
+    float *red = smem;                                   // [n_groups][K][BT] (reuses the tile)
+    if (worker) {
+#pragma unroll
+        for (int b = 0; b < BT; ++b) red[(grp * g.K + k) * BT + b] = acc[b];
+    }
+    __syncthreads();
+    for (int i = tid; i < g.K * BT; i += PD_ROWS) {
+        const int kk = i / BT, b = i - kk * BT;
+        if (b < g.B) {
+            float sum = 0.0f;
+            for (int q = 0; q < n_groups; ++q) sum += red[(q * g.K + kk) * BT + b];
+            red_add(gcoefs + (int64_t)b * g.K + kk, sum);
+        }
+    }
+}
+
 template <int BT>
 static int launch_pca(const float *coefs, const float *basis, const float *mean, float *out, const PcaDims &g,
                       cudaStream_t st) {
@@ -203,9 +282,56 @@ static int launch_pca(const float *coefs, const float *basis, const float *mean,
     return check_launch("pca_decode_kernel");
 }
 
+template <int BT>
+static int launch_pca_bwd(const float *gout, const float *basis, float *gcoefs, const PcaDims &g, cudaStream_t st) {
+    const size_t tile = (size_t)PD_ROWS * pd_pitch(g.K);
+    size_t smem_f = tile + (size_t)PD_ROWS * BT;
+    const size_t red = (size_t)(PD_ROWS / 32 + 1) * g.K * BT;
+    if (red > tile) smem_f += red - tile;
+    const size_t smem = sizeof(float) * smem_f;
+    if (smem > 200 * 1024) { set_error("pca_decode_backward: needs %zu bytes of shared memory", smem); return LR_ERR_BAD_ARGUMENT; }
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(pca_decode_backward_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) { set_error("pca_decode_backward: cannot raise shared memory limit: %s", cudaGetErrorString(e)); return LR_ERR_CUDA; }
+    }
+    int blocks_per_sm = (int)((220 * 1024) / (smem + 1024));
+    if (blocks_per_sm > 8) blocks_per_sm = 8;
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
+    int64_t grid = (int64_t)148 * blocks_per_sm;
+    if (grid > g.n_tiles) grid = g.n_tiles;
+    pca_decode_backward_kernel<BT><<<(unsigned)grid, PD_ROWS, smem, st>>>(gout, basis, gcoefs, g);
+    return check_launch("pca_decode_backward_kernel");
+}
+
 }  // namespace lr
 
 using namespace lr;
+
+extern "C" int lr_pca_decode_backward(const float *grad_out, const float *basis, int B, int K, int64_t N, float *grad_coefs,
+                                      lr_stream_t stream) {
+    LR_REQUIRE(grad_out && basis && grad_coefs, "pca_decode_backward: null pointer");
+    LR_REQUIRE(B > 0 && K > 0 && N > 0, "pca_decode_backward: non-positive dimension (B=%d K=%d N=%lld)", B, K, (long long)N);
+    LR_REQUIRE(K % 4 == 0 && K <= 160 && ((uintptr_t)basis & 15) == 0,
+               "pca_decode_backward: K must be a multiple of 4, <= 160, and the basis 16-byte aligned (got K=%d)", K);
+    PcaDims g;
+    g.K = K; g.N = N; g.add_identity = 0; g.D = g.H = g.W = 0; g.nvox = 1; g.sp0 = g.sp1 = g.sp2 = 0.0;
+    g.n_tiles = (N + PD_ROWS - 1) / PD_ROWS;
+    cudaStream_t st = as_stream(stream);
+    for (int b0 = 0; b0 < B; b0 += 16) {
+        const int nb = B - b0 < 16 ? B - b0 : 16;
+        g.B = nb;
+        const float *go = grad_out + (int64_t)b0 * N;
+        float *gc = grad_coefs + (int64_t)b0 * K;
+        int e;
+        if (nb <= 1) e = launch_pca_bwd<1>(go, basis, gc, g, st);
+        else if (nb <= 2) e = launch_pca_bwd<2>(go, basis, gc, g, st);
+        else if (nb <= 4) e = launch_pca_bwd<4>(go, basis, gc, g, st);
+        else if (nb <= 8) e = launch_pca_bwd<8>(go, basis, gc, g, st);
+        else e = launch_pca_bwd<16>(go, basis, gc, g, st);
+        if (e) return e;
+    }
+    return LR_OK;
+}
 
 extern "C" int lr_pca_decode(const float *coefs, const float *basis, const float *mean, int B, int K, int64_t N,
                              int add_identity, int D, int H, int W, float *out, lr_stream_t stream) {

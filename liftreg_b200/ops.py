@@ -319,8 +319,17 @@ class _PcaDecode(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         (basis,) = ctx.saved_tensors
-        # d/dcoefs = grad_out (B,N) @ basis (N,K): a library GEMM; the basis and the mean are frozen buffers in the model
-        return grad_out @ basis, None, None, None, None, None, None
+        # d/dcoefs = grad_out (B,N) @ basis (N,K): the second pass over the basis; basis and mean are frozen buffers
+        grad_out = _need_cuda_f32(grad_out, "grad_out")
+        B, N = grad_out.shape
+        K = basis.shape[1]
+        if K % 4 != 0 or basis.data_ptr() % 16 != 0:
+            return grad_out @ basis, None, None, None, None, None, None      # odd K: library GEMM
+        gcoefs = torch.zeros((B, K), device=grad_out.device, dtype=torch.float32)
+        with torch.cuda.device(grad_out.device):
+            _native.check(_native.lib().lr_pca_decode_backward(_ptr(grad_out), _ptr(basis), B, K, N, _ptr(gcoefs), _stream()),
+                          "lr_pca_decode_backward")
+        return gcoefs, None, None, None, None, None, None
 
 
 def pca_decode(coefs, pca_vectors, pca_mean=None, img_shape=None, add_identity=False):

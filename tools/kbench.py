@@ -69,7 +69,7 @@ def main():
         _native.check(lib.lr_drr_backward(vp(gdrr), 1, *VOL, ops._dp(p64), 1, P, 240, 240, ops._fp(sp3), 0,
                                           ctypes.c_float(0.1), vp(s["gvol"]), st), "drr_bwd")
 
-    if "pca" in which:
+    if "pca" in which or "pca_bwd" in which:
         K = 56
         basis = torch.empty((3 * nv, K), device=dev).normal_(0, 1e-3)       # 2.75 GB, as the model holds it
         pmean = torch.zeros(3 * nv, device=dev)
@@ -78,10 +78,18 @@ def main():
         for i, s_ in enumerate(sets):
             s_["pout"] = pout[i]
 
+    if "pca_bwd" in which:
+        pgout = torch.randn(1, 3 * nv, device=dev)
+        pgc = torch.zeros(1, 56, device=dev)
+
+    def k_pca_bwd(s, st):
+        _native.check(lib.lr_pca_decode_backward(vp(pgout), vp(basis), 1, 56, 3 * nv, vp(pgc), st), "pca_bwd")
+
     def k_pca(s, st):
         _native.check(lib.lr_pca_decode(vp(coefs), vp(basis), vp(pmean), 1, K, 3 * nv, 1, *VOL, vp(s["pout"]), st), "pca")
 
-    units = {"warp": (k_warp, nv, 20 * nv), "pca": (k_pca, 3 * nv, 4 * 3 * nv * 56 + 8 * 3 * nv), "warp_bwd": (k_warp_bwd, nv, 32 * nv),
+    units = {"warp": (k_warp, nv, 20 * nv), "pca": (k_pca, 3 * nv, 4 * 3 * nv * 56 + 8 * 3 * nv),
+             "pca_bwd": (k_pca_bwd, 3 * nv, 4 * 3 * nv * 56 + 4 * 3 * nv), "warp_bwd": (k_warp_bwd, nv, 32 * nv),
              "drr_bwd": (k_drr_bwd, P * 240 * 240 * VOL[1], 4 * nv + 4 * P * 240 * 240), "backproject": (k_backproject, P * nv, 4 * P * nv + 4 * P * DET[0] * DET[1]),
              "drr": (k_drr, P * 240 * 240 * VOL[1], 4 * nv + 4 * P * 240 * 240)}
     for name in which:
