@@ -40,6 +40,20 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_variant(name, defines):
+    """Kernel experiments: compile with extra -D flags into _lib/variants/<name>.so (use via LIFTREG_B200_LIB)."""
+    out = os.path.join(LIB_DIR, "variants", name + ".so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    env = dict(os.environ)
+    env.pop("CC", None)
+    env.pop("CXX", None)
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", out]
+    res = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    return out
+
+
 def build(force=False, verbose=False):
     """Compile every CUDA source into one shared library. Returns the path."""
     if not force and not needs_build():
@@ -62,4 +76,8 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
+    if "--variant" in sys.argv:          # python -m liftreg_b200.build --variant NAME [DEFINE=VALUE ...]
+        k = sys.argv.index("--variant")
+        print(build_variant(sys.argv[k + 1], sys.argv[k + 2:]))
+        sys.exit(0)
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -29,6 +29,18 @@ int check_launch(const char *what) {
     return LR_OK;
 }
 
+int sm_count() {
+    static thread_local int cached_dev = -1, cached_n = 148;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return cached_n; }
+    if (dev != cached_dev) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) { cached_n = n; cached_dev = dev; }
+        else cudaGetLastError();
+    }
+    return cached_n;
+}
+
 static size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
 
 // Pinned (page-locked, mapped) host memory can be read / written by kernels directly over PCIe (UVA).  The host

@@ -15,6 +15,9 @@
 // (lanes along h: coalesced 128 B stores, near-contiguous gathers), keeps its v-part in registers and walks a
 // chunk of i; the per-i u-part comes from a small shared-memory table built once per block.  The batch loop is
 // innermost, so geometry and weights are shared by all B items.
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace lr {
@@ -33,6 +36,14 @@ struct BpDims {
     int B, P, pw, ph, d, w, h;     // d = planes of axis 0 held by the output (the whole volume, or a z-slab of it)
     int i_off;                     // absolute index of the output's first plane (0 unless slab-sharded)
     int ichunk;                    // planes per block: ceil(d / ceil(d / BP_ICHUNK)) <= BP_ICHUNK
+    int isub;                      // forward: planes per sub-chunk (one blockDim.y slice); the row window restarts there
+    int hp;                        // forward: ceil(h / 2), the distance between the two voxels a thread owns
+    int bx, by;                    // forward: group shape (column pairs x sub-chunks)
+    // forward: blocks walk runs of consecutive coronal rows j, in three sizes, longest first (blocks are dispatched in
+    // index order, so the last ones to start are the short ones and the tail of the launch drains quickly):
+    // nj0 runs of js0 rows, then nj1 of js1, then nj2 of js2, each for every (view, chunk)
+    int js0, js1, js2, nj0, nj1, nj2;
+    int n_chunks, n_vc;            // forward: chunks of planes; views * chunks
     int p0;                        // first view of this launch
     float half_d, half_h;          // d/2, h/2 (exact)
     ConstDiv div_pw, div_ph;       // division by (float)pw, (float)ph via Markstein (bit-identical to IEEE division)
@@ -81,11 +92,11 @@ struct __align__(8) BpRow8 {
     int packed;     // (off0 << 5) | window flags (bits 2..4 of BpRow::mask)
 };
 
-// Builds the tables; returns (block-uniformly) whether every plane of the chunk has both rows inside the detector.
+// Builds the tables; returns whether every plane this thread handled has both rows inside the detector.
 __device__ __forceinline__ bool build_row_table(BpRow *rows, BpRow8 *rows8, const BpDims &g, int i_begin, int i_count,
-                                                float sx, float scale) {
+                                                float sx, float scale, int isub, int tid, int n_thr) {
     int ok = 1;
-    for (int t_idx = threadIdx.x; t_idx < i_count; t_idx += blockDim.x) {
+    for (int t_idx = tid; t_idx < i_count; t_idx += n_thr) {
         AxisTap t = axis_tap((float)(g.i_off + i_begin + t_idx) - g.half_d, sx, scale, g.div_pw, g.hpw);
         BpRow r;
         r.off0 = t.i0 * g.ph;
@@ -95,7 +106,7 @@ __device__ __forceinline__ bool build_row_table(BpRow *rows, BpRow8 *rows8, cons
         ok &= r.mask == 3;
         // consecutive planes advance the detector row by ~1..1.4 (the magnification): tell the consumer how far
         int step = 2;
-        if (t_idx > 0) {
+        if (t_idx % isub != 0) {
             const AxisTap tp = axis_tap((float)(g.i_off + i_begin + t_idx - 1) - g.half_d, sx, scale, g.div_pw, g.hpw);
             const int dlt = t.i0 - tp.i0;
             step = (dlt == 0 || dlt == 1) ? dlt : 2;
@@ -109,7 +120,7 @@ __device__ __forceinline__ bool build_row_table(BpRow *rows, BpRow8 *rows8, cons
             rows8[t_idx] = c;
         }
     }
-    return __syncthreads_and(ok) != 0;
+    return ok != 0;       // this thread's entries only: the caller reduces over the group
 }
 
 // ATen vector kernel: out = fma(se_v, n*w, fma(sw_v, n*e, fma(ne_v, s*w, nw_v * (s*e))))
@@ -118,84 +129,123 @@ __device__ __forceinline__ float bilerp(float va, float vb, float vc, float vd, 
     return fma_rn(vd, se, fma_rn(vc, sw, fma_rn(vb, ne, mul_rn(va, nw))));
 }
 
+// Zeros-padding path of one voxel column (k): per-tap predicates, scalar arithmetic.
+__device__ __forceinline__ void backproject_column_checked(const float *pvf, char *o, int64_t plane_bytes, const BpRow *rows,
+                                                           int ii0, int ii1, int ph, bool c0, bool c1, float e, float wq) {
+    for (int ii = ii0; ii < ii1; ++ii) {
+        const BpRow r = rows[ii];
+        const float *q0 = pvf + r.off0;
+        const float *q1 = q0 + ph;
+        const bool rv0 = (r.mask & 1) != 0, rv1 = (r.mask & 2) != 0;
+        const float va = (rv0 && c0) ? __ldg(q0) : 0.0f, vb = (rv0 && c1) ? __ldg(q0 + 1) : 0.0f;
+        const float vc = (rv1 && c0) ? __ldg(q1) : 0.0f, vd = (rv1 && c1) ? __ldg(q1 + 1) : 0.0f;
+        st_stream((float *)o, bilerp(va, vb, vc, vd, r.s, r.n, e, wq));
+        o += plane_bytes;
+    }
+}
+
+// Block = (view p, chunk of planes i, group of g.jb consecutive coronal rows j); threads = (g.bx column pairs) x
+// (g.by sub-chunks of g.isub planes).  A thread owns TWO voxel columns k0 = q and k1 = q + ceil(h/2) (both
+// warp-contiguous, so loads and stores coalesce exactly as with one column) and evaluates them as one packed fp32x2
+// stream; the per-plane table entry, flags and weights are shared by the pair.  The rows j of the group are walked
+// inside the block: everything that does not depend on j (pointers, centred coordinates, plane range) is set up once
+// -- with one row per block that set-up was 36 % of all executed instructions (ncu source counters).
 __global__ void __launch_bounds__(256)
     backproject_forward_kernel(const float *__restrict__ proj, float *__restrict__ out, BpDims g, BpPoses poses) {
-    __shared__ BpRow rows[BP_ICHUNK];
-    __shared__ BpRow8 rows8[BP_ICHUNK];
+    __shared__ BpRow rows_all[2][BP_ICHUNK];
+    __shared__ BpRow8 rows8_all[2][BP_ICHUNK];
+    __shared__ float scale_all[2];
 
-    const int j = blockIdx.x;
-    const int i_begin = blockIdx.y * g.ichunk;
-    const int pl = blockIdx.z;           // view inside this launch
-    const int p = g.p0 + pl;
-    const float sx = poses.s[pl][0], sy = poses.s[pl][1], sz = poses.s[pl][2];
-    const int i_count = min(g.ichunk, g.d - i_begin);
-    // Block set-up used to cost as much as the sample loop (ablation: 11.7 of 25.6 us with the loop removed): every
-    // thread ran three IEEE divisions.  Now the only true division (scale = sy / (sy - y_j), block-uniform) is done by
-    // the table-building threads and broadcast through shared memory; /pw and /ph are Markstein multiplications.
-    __shared__ float s_scale;
-    float scale = 0.0f;
-    if ((int)threadIdx.x < i_count || threadIdx.x == 0) {
-        scale = view_scale(sy, g.w, j);
-        if (threadIdx.x == 0) s_scale = scale;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, n_thr = blockDim.x * blockDim.y;
+    // block index -> (run of rows, chunk, view): level-major, then (view, chunk), the run fastest (neighbouring blocks
+    // gather from neighbouring detector patches)
+    int L = blockIdx.x, nj = g.nj0, js = g.js0, j_base = 0;
+    if (L >= g.nj0 * g.n_vc) {
+        L -= g.nj0 * g.n_vc; nj = g.nj1; js = g.js1; j_base = g.nj0 * g.js0;
+        if (L >= g.nj1 * g.n_vc) { L -= g.nj1 * g.n_vc; nj = g.nj2; js = g.js2; j_base += g.nj1 * g.js1; }
     }
-    const bool rows_ok = build_row_table(rows, rows8, g, i_begin, i_count, sx, scale);
-    scale = s_scale;
-
+    const int vc = L / nj;
+    const int pl = vc / g.n_chunks;      // view inside this launch
+    const int p = g.p0 + pl;
+    const int i_begin = (vc - pl * g.n_chunks) * g.ichunk;
+    const int i_count = min(g.ichunk, g.d - i_begin);
+    const int j_begin = j_base + (L - vc * nj) * js, j_end = min(g.w, j_begin + js);
+    const float sx = poses.s[pl][0], sy = poses.s[pl][1], sz = poses.s[pl][2];
+    const int ii0 = threadIdx.y * g.isub, ii1 = min(i_count, ii0 + g.isub);    // this thread's planes of the chunk
     const int64_t proj_batch = (int64_t)g.P * g.proj_view_stride;
     const int64_t plane_bytes = (int64_t)g.w * g.h * 4;
-    for (int k = threadIdx.x; k < g.h; k += blockDim.x) {
-        const AxisTap tv = axis_tap((float)k - g.half_h, sz, scale, g.div_ph, g.hph);
-        const float wq = tv.w1, e = sub_rn(1.0f, wq);
-        const bool c0 = (unsigned)tv.i0 < (unsigned)g.ph, c1 = (unsigned)(tv.i0 + 1) < (unsigned)g.ph;
-        // geometry (table + v-part) is shared by all batch items; the batch loop is the outer one so that the
-        // per-sample inner loop stays branch-free: LDS.128, 4 weights, 4 loads, 1 mul + 3 fma, 1 store
+    const unsigned plane = (unsigned)(g.w * g.h);
+    const float *pv0 = proj + (int64_t)p * g.proj_view_stride;
+    float *ob0 = out + (int64_t)p * g.out_chan_stride + (int64_t)i_begin * g.w * g.h;
+
+    for (int j = j_begin; j < j_end; ++j) {
+        const int buf = (j - j_begin) & 1;
+        BpRow *rows = rows_all[buf];
+        BpRow8 *rows8 = rows8_all[buf];
+        // The only true division (scale = sy / (sy - y_j), block-uniform) is done by the table-building threads and
+        // broadcast through shared memory; /pw and /ph are Markstein multiplications.
+        float scale = 0.0f;
+        if (tid < i_count || tid == 0) {
+            scale = view_scale(sy, g.w, j);
+            if (tid == 0) scale_all[buf] = scale;
+        }
+        // double-buffered table: one barrier per row (no thread can be more than one row ahead of the slowest one)
+        const bool rows_ok = __syncthreads_and(build_row_table(rows, rows8, g, i_begin, i_count, sx, scale, g.isub, tid, n_thr));
+        scale = scale_all[buf];
+
+        for (int q = threadIdx.x; q < g.hp; q += blockDim.x) {
+            const int k0 = q, k1 = q + g.hp;
+            const bool has1 = k1 < g.h;
+            const AxisTap t0 = axis_tap((float)k0 - g.half_h, sz, scale, g.div_ph, g.hph);
+            const AxisTap t1 = axis_tap((float)(has1 ? k1 : k0) - g.half_h, sz, scale, g.div_ph, g.hph);
+            const float wq0 = t0.w1, e0 = sub_rn(1.0f, wq0), wq1 = t1.w1, e1 = sub_rn(1.0f, wq1);
+            const bool c00 = (unsigned)t0.i0 < (unsigned)g.ph, c01 = (unsigned)(t0.i0 + 1) < (unsigned)g.ph;
+            const bool c10 = (unsigned)t1.i0 < (unsigned)g.ph, c11 = (unsigned)(t1.i0 + 1) < (unsigned)g.ph;
+            // geometry (table + v-part) is shared by all batch items
 #pragma unroll 1
-        for (int b = 0; b < g.B; ++b) {
-            const float *pvf = proj + b * proj_batch + (int64_t)p * g.proj_view_stride + tv.i0;
-            char *o = (char *)(out + b * g.out_batch_stride + (int64_t)p * g.out_chan_stride +
-                               ((int64_t)i_begin * g.w + j) * g.h + k);
-            if (rows_ok && c0 && c1) {
-                // every tap of every plane of this chunk is inside the detector (the common case).
-                // Sliding window over detector rows: this thread's two columns of rows r0, r0+1 stay in registers;
-                // when the next plane moves one row down only the new row is fetched (2.4 loads / sample on average
-                // instead of 4 -- the kernel is bound by L1 wavefronts, ncu: lsu data-pipe 68 %).
-                // The step (0, 1 or 2+ rows) is block-uniform; it is applied with predicated moves / loads rather
-                // than branches, which keeps the loop body straight-line (~23 SASS per sample).
-                const float *base = opaque(pvf);      // row offsets are non-negative here: one IMAD.WIDE.U32 per pointer
-                float va = 0.0f, vb = 0.0f, vc = 0.0f, vd = 0.0f;
-                const f32x2 e2 = splat2(e), w2 = splat2(wq);
+            for (int b = 0; b < g.B; ++b) {
+                const float *pv = pv0 + b * proj_batch;
+                float *ob = ob0 + b * g.out_batch_stride + (unsigned)(j * g.h);
+                if (rows_ok && has1 && c00 && c01 && c10 && c11) {
+                    // every tap of every plane of this chunk is inside the detector (the common case).
+                    // Sliding window over detector rows: the pair's two columns of rows r0, r0+1 stay in registers;
+                    // when the next plane moves one row down only the new row is fetched (2.4 loads / sample on
+                    // average instead of 4).  The step (0, 1 or 2+ rows) is block-uniform; it is applied with
+                    // predicated moves / loads rather than branches, which keeps the loop body straight-line.
+                    const float *lo0 = opaque(pv + t0.i0), *lo1 = opaque(pv + t1.i0);         // row r0 of each column
+                    const float *up0 = opaque(lo0 + g.ph), *up1 = opaque(lo1 + g.ph);         // row r0 + 1
+                    float *o0 = opaque(ob + k0), *o1 = opaque(ob + k1);
+                    unsigned ofs = (unsigned)ii0 * plane;
+                    f32x2 va = 0, vb = 0, vc = 0, vd = 0;           // (column k0, column k1) of taps nw, ne, sw, se
+                    const f32x2 e2 = pack2(e0, e1), w2 = pack2(wq0, wq1);
 #pragma unroll 4
-                for (int ii = 0; ii < i_count; ++ii) {
-                    const BpRow8 r = rows8[ii];
-                    const unsigned off0 = (unsigned)r.packed >> 5;
-                    if (r.packed & 4) { va = vc; vb = vd; }   // moved exactly one row down: reuse the upper row
-                    if (r.packed & 8) {                       // moved further (or first plane): fetch the lower row too
-                        const float *q0 = base + off0;
-                        va = __ldg(q0); vb = __ldg(q0 + 1);
+                    for (int ii = ii0; ii < ii1; ++ii) {
+                        const BpRow8 r = rows8[ii];
+                        const unsigned off0 = (unsigned)r.packed >> 5;
+                        if (r.packed & 4) { va = vc; vb = vd; }   // moved exactly one row down: reuse the upper row
+                        if (r.packed & 8) {                       // moved further (or first plane): fetch the lower row too
+                            const float *q0 = lo0 + off0, *q1 = lo1 + off0;
+                            va = pack2(__ldg(q0), __ldg(q1)); vb = pack2(__ldg(q0 + 1), __ldg(q1 + 1));
+                        }
+                        if (r.packed & 16) {
+                            const float *q0 = up0 + off0, *q1 = up1 + off0;
+                            vc = pack2(__ldg(q0), __ldg(q1)); vd = pack2(__ldg(q0 + 1), __ldg(q1 + 1));
+                        }
+                        const f32x2 n2 = splat2(r.n), s2 = splat2(sub_rn(1.0f, r.n));
+                        const f32x2 nw = mul2(s2, e2), ne = mul2(s2, w2), sw = mul2(n2, e2), se = mul2(n2, w2);
+                        float r0v, r1v;
+                        unpack2(fma2(vd, se, fma2(vc, sw, fma2(vb, ne, mul2(va, nw)))), r0v, r1v);
+                        st_stream(o0 + ofs, r0v);
+                        st_stream(o1 + ofs, r1v);
+                        ofs += plane;
                     }
-                    if (r.packed & 16) {
-                        const float *q1 = base + (off0 + (unsigned)g.ph);
-                        vc = __ldg(q1); vd = __ldg(q1 + 1);
-                    }
-                    // weights (n,s) x e and (n,s) x w as two packed products: (sw, nw) and (se, ne)
-                    float sw, nw, se, ne;
-                    const f32x2 ns = pack2(r.n, sub_rn(1.0f, r.n));
-                    unpack2(mul2(ns, e2), sw, nw);
-                    unpack2(mul2(ns, w2), se, ne);
-                    st_stream((float *)o, fma_rn(vd, se, fma_rn(vc, sw, fma_rn(vb, ne, mul_rn(va, nw)))));
-                    o += plane_bytes;
-                }
-            } else {
-                // rays leaving the detector: per-tap predicates (zeros padding)
-                for (int ii = 0; ii < i_count; ++ii) {
-                    const BpRow r = rows[ii];
-                    const float *q0 = pvf + r.off0;
-                    const float *q1 = q0 + g.ph;
-                    const bool rv0 = (r.mask & 1) != 0, rv1 = (r.mask & 2) != 0;
-                    const float va = (rv0 && c0) ? __ldg(q0) : 0.0f, vb = (rv0 && c1) ? __ldg(q0 + 1) : 0.0f;
-                    const float vc = (rv1 && c0) ? __ldg(q1) : 0.0f, vd = (rv1 && c1) ? __ldg(q1 + 1) : 0.0f;
-                    st_stream((float *)o, bilerp(va, vb, vc, vd, r.s, r.n, e, wq));
-                    o += plane_bytes;
+                } else {
+                    // rays leaving the detector: per-tap predicates (zeros padding)
+                    backproject_column_checked(pv + t0.i0, (char *)(ob + k0) + ii0 * plane_bytes, plane_bytes, rows, ii0, ii1,
+                                               g.ph, c00, c01, e0, wq0);
+                    if (has1)
+                        backproject_column_checked(pv + t1.i0, (char *)(ob + k1) + ii0 * plane_bytes, plane_bytes, rows, ii0,
+                                                   ii1, g.ph, c10, c11, e1, wq1);
                 }
             }
         }
@@ -213,7 +263,8 @@ __global__ void __launch_bounds__(256)
     const float sx = poses.s[pl][0], sy = poses.s[pl][1], sz = poses.s[pl][2];
     const float scale = view_scale(sy, g.w, j);
     const int i_count = min(g.ichunk, g.d - i_begin);
-    build_row_table(rows, nullptr, g, i_begin, i_count, sx, scale);
+    build_row_table(rows, nullptr, g, i_begin, i_count, sx, scale, g.ichunk, threadIdx.x, blockDim.x);
+    __syncthreads();
     float *pv = gproj + (int64_t)p * g.proj_view_stride;
     const int64_t proj_batch = (int64_t)g.P * g.proj_view_stride;
     const int plane = g.w * g.h;
@@ -273,6 +324,8 @@ static int fill_dims(BpDims &g, int B, int P, int pw, int ph, int d_total, int w
     const int n_chunks = (d + BP_ICHUNK - 1) / BP_ICHUNK;
     g.ichunk = (((d + n_chunks - 1) / n_chunks + 3) / 4) * 4;      // balanced, multiple of the unroll factor
     if (g.ichunk > BP_ICHUNK) g.ichunk = BP_ICHUNK;
+    g.isub = g.ichunk; g.hp = (h + 1) / 2; g.bx = g.by = 1;
+    g.js0 = g.js1 = g.js2 = 1; g.nj0 = w; g.nj1 = g.nj2 = 0; g.n_chunks = g.n_vc = 1;
     g.half_d = (float)((double)d_total / 2.0); g.half_h = (float)((double)h / 2.0);
     g.div_pw = make_const_div((float)pw); g.div_ph = make_const_div((float)ph);
     g.hpw = (float)(pw - 1) / 2.0f; g.hph = (float)(ph - 1) / 2.0f;
@@ -284,6 +337,50 @@ static int fill_dims(BpDims &g, int B, int P, int pw, int ph, int d_total, int w
 static int block_threads(int h) {
     int t = ((h + 31) / 32) * 32;
     return t < 32 ? 32 : (t > 256 ? 256 : t);
+}
+
+#ifndef LR_BP_ISUB
+#define LR_BP_ISUB 16
+#endif
+#ifndef LR_BP_FWD_THREADS
+#define LR_BP_FWD_THREADS 192
+#endif
+// Forward launch shape.  Block = (column pairs: ceil(h/2), at most 256) x (sub-chunks of the chunk's planes); each block
+// walks a run of consecutive rows j.  Long runs amortise the per-block set-up, but a block of 4 rows lives ~7 us of a
+// ~25 us launch, the kernel is latency-bound (throughput follows occupancy) and the grid is only a few waves, so with
+// equal blocks the launch ends with every SM draining from 6 resident blocks to 0 over a whole block duration.  The
+// runs therefore taper: 4 rows, then 2, then 1.
+static dim3 forward_shape(BpDims &g, int n_views, unsigned &grid) {
+    static int f0 = -1, f1 = -1;        // percent of the rows in 4-row / 2-row runs (the rest: single rows)
+    if (f0 < 0) {
+        int a = 50, b = 30;
+        if (const char *e = getenv("LIFTREG_B200_BP_TAPER")) sscanf(e, "%d,%d", &a, &b);   // kernel experiments
+        f1 = b; f0 = a;
+    }
+    g.hp = (g.h + 1) / 2;
+    g.bx = g.hp > 256 ? 256 : g.hp;
+    int by = LR_BP_FWD_THREADS / g.bx;
+    if (by < 1) by = 1;
+    int isub = LR_BP_ISUB;
+    if (by * isub > BP_ICHUNK) by = BP_ICHUNK / isub;
+    const int per_item = by * isub;
+    const int n_chunks0 = (g.d + per_item - 1) / per_item;                    // balance the chunks over the planes
+    isub = (((g.d + n_chunks0 - 1) / n_chunks0 + by - 1) / by + 3) / 4 * 4;   // multiple of the unroll factor
+    if (isub > LR_BP_ISUB) isub = LR_BP_ISUB;
+    g.by = by;
+    g.isub = isub;
+    g.ichunk = isub * by;
+    g.n_chunks = (g.d + g.ichunk - 1) / g.ichunk;
+    g.n_vc = g.n_chunks * n_views;
+    g.js0 = 4; g.js1 = 2; g.js2 = 1;
+    g.nj0 = (g.w * f0 / 100) / g.js0;
+    int rest = g.w - g.nj0 * g.js0;
+    g.nj1 = f0 + f1 >= 100 ? (rest + g.js1 - 1) / g.js1 : (g.w * f1 / 100) / g.js1;
+    if (g.nj1 * g.js1 > rest) g.nj1 = (rest + g.js1 - 1) / g.js1;
+    rest -= g.nj1 * g.js1;
+    g.nj2 = rest > 0 ? rest : 0;
+    grid = (unsigned)((g.nj0 + g.nj1 + g.nj2) * g.n_vc);
+    return dim3((unsigned)g.bx, (unsigned)g.by, 1);
 }
 
 }  // namespace lr
@@ -304,8 +401,9 @@ extern "C" int lr_backproject_forward_slab(const float *proj, const float *poses
         for (int q = 0; q < np; ++q)
             for (int c = 0; c < 3; ++c) ps.s[q][c] = poses[(p0 + q) * 3 + c];
         g.p0 = p0;
-        dim3 grid((unsigned)w, (unsigned)((d + g.ichunk - 1) / g.ichunk), (unsigned)np);
-        backproject_forward_kernel<<<grid, block_threads(h), 0, as_stream(stream)>>>(proj, out, g, ps);
+        unsigned grid;
+        const dim3 block = forward_shape(g, np, grid);
+        backproject_forward_kernel<<<grid, block, 0, as_stream(stream)>>>(proj, out, g, ps);
         if (int e = check_launch("backproject_forward_kernel")) return e;
     }
     return LR_OK;

@@ -152,6 +152,7 @@ __device__ __forceinline__ void red_add(float *p, float v) {
 namespace lr {
 void set_error(const char *fmt, ...);
 int check_launch(const char *what);  // cudaGetLastError -> lr_status; bumps the per-thread launch counter
+int sm_count();                      // multiprocessors of the current device (cached per device)
 inline cudaStream_t as_stream(lr_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 }  // namespace lr
 

@@ -8,6 +8,9 @@
 // local gather served by L1/L2.  Arithmetic follows ATen's CPU grid_sampler_3d exactly: unnormalise
 // ((g+1)/2)*(S-1), weights (x1-x)*(y1-y)*(z1-z) left to right, taps accumulated in the order
 // tnw,tne,tsw,tse,bnw,bne,bsw,bse with separately rounded multiply and add.
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace lr {
@@ -15,7 +18,8 @@ namespace lr {
 constexpr int WARP_TX = 32;   // threads along W (coalesced 128 B rows)
 constexpr int WARP_TY = 8;    // thread rows per block
 constexpr int WARP_VY = 2;    // forward: output rows per thread (y and y + WARP_TY), processed as packed fp32x2
-constexpr int WARP_NZ = 4;    // forward: consecutive planes per block (software-pipelined phi loads)
+constexpr int WARP_NZ = 4;    // forward: default consecutive planes per block (software-pipelined phi loads)
+constexpr int WARP_NZ_MAX = 8;   // forward: planes per block of the long blocks (see forward_z_blocking)
 
 struct WarpDims {
     int C, D, H, W;
@@ -24,7 +28,11 @@ struct WarpDims {
     // Output slab (multi-GPU z-slab sharding): phi / out / grad_out / grad_phi hold planes [z_off, z_off+Do) of
     // axis 0 only, i.e. they are (B,*,Do,H,W) tensors; the image (and grad_img) is always the full (B,C,D,H,W).
     int Do, z_off, nvox_o;
-    int zblocks;         // blocks along z per batch item: Do for the 1-plane kernels, ceil(Do / WARP_NZ) for the forward
+    int zblocks;         // blocks along z per batch item: Do for the 1-plane kernels, ceil(Do / nz) for the forward
+    // forward: z-blocks of a batch item come in three sizes, largest first (blocks are dispatched in index order, so
+    // the last ones to start are the short ones and the tail of the launch drains quickly): n0 blocks of s0 planes,
+    // then n1 of s1, then the rest of s2
+    int zs0, zs1, zs2, zn0, zn1;
     unsigned z_magic;    // ceil(2^32 / zblocks): b = (blockIdx.z * z_magic) >> 32 for blockIdx.z < 65536
     float hx, hy, hz;    // (W-1)/2, (H-1)/2, (D-1)/2
     float mx, my, mz;    // W-1, H-1, D-1
@@ -156,34 +164,50 @@ __device__ __forceinline__ void warp_pair(const float *__restrict__ src, float *
             const f32x2 wy1 = sub2(iy, fy), wy0 = sub2(add2(fy, one), iy);
             const f32x2 wz1 = sub2(iz, fz), wz0 = sub2(add2(fz, one), iz);
             const f32x2 a00 = mul2(wx0, wy0), a10 = mul2(wx1, wy0), a01 = mul2(wx0, wy1), a11 = mul2(wx1, wy1);
-            const f32x2 wt[8] = {mul2(a00, wz0), mul2(a10, wz0), mul2(a01, wz0), mul2(a11, wz0),
-                                 mul2(a00, wz1), mul2(a10, wz1), mul2(a01, wz1), mul2(a11, wz1)};
+            // net_utils.py:50 samples (img+1)/2: the exact scaling by 1/2 commutes with every rounding below (no
+            // underflow: weights are products of three fractions >= 2^-24), so it is applied once to the two z
+            // weights instead of to each of the 8 tap values; the "+1" stays per tap.
+            const f32x2 half = splat2(0.5f);
+            const f32x2 wz0s = SCALE ? mul2(wz0, half) : wz0, wz1s = SCALE ? mul2(wz1, half) : wz1;
+            const f32x2 wt[8] = {mul2(a00, wz0s), mul2(a10, wz0s), mul2(a01, wz0s), mul2(a11, wz0s),
+                                 mul2(a00, wz1s), mul2(a10, wz1s), mul2(a01, wz1s), mul2(a11, wz1s)};
             const bool la = x0a >= 0, ha = x0a < g.W - 1, lb = x0b >= 0, hb = x0b < g.W - 1;   // x taps inside?
+            // Only the lanes next to an x face ever mask a tap; when no lane of the warp does (a vote over whichever
+            // lanes are here -- both variants compute the same values), the taps load unpredicated, straight into the
+            // packed register pairs, without the preset constants and moves of the masked form.
+            const bool all_in = __all_sync(__activemask(), la && ha && lb && hb);
             // signed 32-bit element offsets (x0 may be -1): each row pointer is one IMAD.WIDE off an opaque base
             const int a0 = z0a * g.HW + y0a * g.W + x0a, b0 = z0b * g.HW + y0b * g.W + x0b;
             const int a1 = a0 + g.W, a2 = a0 + g.HW, a3 = a2 + g.W;
             const int b1 = b0 + g.W, b2 = b0 + g.HW, b3 = b2 + g.W;
-            const f32x2 half = splat2(0.5f), two = splat2(2.0f), zero = splat2(g.zero);
+            const f32x2 two = splat2(2.0f), zero = splat2(g.zero);
 #pragma unroll 1
             for (int c = 0; c < nchan; ++c) {
                 const float *sc = opaque(src + (int64_t)c * g.nvox);
                 const float *pa0 = sc + a0, *pa1 = sc + a1, *pa2 = sc + a2, *pa3 = sc + a3;
                 const float *pb0 = sc + b0, *pb1 = sc + b1, *pb2 = sc + b2, *pb3 = sc + b3;
                 f32x2 v[8];
+                if (all_in) {
+                    v[0] = pack2(__ldg(pa0), __ldg(pb0)); v[1] = pack2(__ldg(pa0 + 1), __ldg(pb0 + 1));
+                    v[2] = pack2(__ldg(pa1), __ldg(pb1)); v[3] = pack2(__ldg(pa1 + 1), __ldg(pb1 + 1));
+                    v[4] = pack2(__ldg(pa2), __ldg(pb2)); v[5] = pack2(__ldg(pa2 + 1), __ldg(pb2 + 1));
+                    v[6] = pack2(__ldg(pa3), __ldg(pb3)); v[7] = pack2(__ldg(pa3 + 1), __ldg(pb3 + 1));
+                } else {
 // masked tap: a value whose (rescaled) intensity is exactly 0: -1 when sampling (img+1)/2, else 0
 #define LR_TAP(p, ok) ((ok) ? __ldg(p) : (SCALE ? -1.0f : 0.0f))
-                v[0] = pack2(LR_TAP(pa0, la), LR_TAP(pb0, lb)); v[1] = pack2(LR_TAP(pa0 + 1, ha), LR_TAP(pb0 + 1, hb));
-                v[2] = pack2(LR_TAP(pa1, la), LR_TAP(pb1, lb)); v[3] = pack2(LR_TAP(pa1 + 1, ha), LR_TAP(pb1 + 1, hb));
-                v[4] = pack2(LR_TAP(pa2, la), LR_TAP(pb2, lb)); v[5] = pack2(LR_TAP(pa2 + 1, ha), LR_TAP(pb2 + 1, hb));
-                v[6] = pack2(LR_TAP(pa3, la), LR_TAP(pb3, lb)); v[7] = pack2(LR_TAP(pa3 + 1, ha), LR_TAP(pb3 + 1, hb));
+                    v[0] = pack2(LR_TAP(pa0, la), LR_TAP(pb0, lb)); v[1] = pack2(LR_TAP(pa0 + 1, ha), LR_TAP(pb0 + 1, hb));
+                    v[2] = pack2(LR_TAP(pa1, la), LR_TAP(pb1, lb)); v[3] = pack2(LR_TAP(pa1 + 1, ha), LR_TAP(pb1 + 1, hb));
+                    v[4] = pack2(LR_TAP(pa2, la), LR_TAP(pb2, lb)); v[5] = pack2(LR_TAP(pa2 + 1, ha), LR_TAP(pb2 + 1, hb));
+                    v[6] = pack2(LR_TAP(pa3, la), LR_TAP(pb3, lb)); v[7] = pack2(LR_TAP(pa3 + 1, ha), LR_TAP(pb3 + 1, hb));
 #undef LR_TAP
+                }
                 // ATen: out += val * w per tap, product and sum rounded separately, in tap order (mul2_sep keeps ptxas
                 // from contracting the pair into one FFMA2)
                 f32x2 acc = splat2(0.0f);
 #pragma unroll
                 for (int t = 0; t < 8; ++t) {
                     f32x2 val = v[t];
-                    if (SCALE) val = mul2(add2(val, one), half);   // net_utils.py:50 (img+1)/2, fused per tap
+                    if (SCALE) val = add2(val, one);               // net_utils.py:50 (img+1)/2; the /2 lives in wt[]
                     acc = add2(acc, mul2_sep(val, wt[t], zero));
                 }
                 if (SCALE) acc = sub2(mul2(acc, two), one);        // net_utils.py:52 (x2 is exact: fusing is harmless)
@@ -200,19 +224,23 @@ __device__ __forceinline__ void warp_pair(const float *__restrict__ src, float *
 }
 
 // Forward kernel.  Thread (tx, ty) of block (bx, by, bz) owns output voxels (x, y, z) and (x, y + WARP_TY, z) for
-// WARP_NZ consecutive planes z.  The map values of plane z+1 are fetched into registers before plane z is
+// a run of consecutive planes z (8, 4 or 2: forward_z_blocking).  The map values of plane z+1 are fetched into registers before plane z is
 // processed, so the HBM latency of the phi stream (the only compulsory traffic besides the store) is hidden behind a
 // whole plane of arithmetic instead of being exposed once per voxel.
 template <int PAD, int MODE, bool SCALE, bool IDENT, bool C1>
-__global__ void __launch_bounds__(WARP_TX * WARP_TY)
+__global__ void __launch_bounds__(WARP_TX * WARP_TY, 4)   // 64 registers: 4 resident blocks per SM
     warp_forward_kernel(const float *__restrict__ img, const float *__restrict__ phi, float *__restrict__ out, WarpDims g) {
     __shared__ IdentTable<WARP_TY * WARP_VY> ident;
-    __shared__ float ident_z[WARP_NZ];
+    __shared__ float ident_z[WARP_NZ_MAX];
     const int x = blockIdx.x * WARP_TX + threadIdx.x;
     const int ya = blockIdx.y * (WARP_TY * WARP_VY) + threadIdx.y;
     const int b = g.zblocks == 1 ? (int)blockIdx.z : (int)__umulhi(blockIdx.z, g.z_magic);   // 2^32/1 does not fit the magic
-    const int z_first = (blockIdx.z - b * g.zblocks) * WARP_NZ;     // first plane (inside the output slab) of this block
-    const int nz = min(WARP_NZ, g.Do - z_first);
+    const int zb = blockIdx.z - b * g.zblocks;
+    int z_first, zsize;                                             // first plane (inside the output slab) of this block
+    if (zb < g.zn0) { z_first = zb * g.zs0; zsize = g.zs0; }
+    else if (zb < g.zn0 + g.zn1) { z_first = g.zn0 * g.zs0 + (zb - g.zn0) * g.zs1; zsize = g.zs1; }
+    else { z_first = g.zn0 * g.zs0 + g.zn1 * g.zs1 + (zb - g.zn0 - g.zn1) * g.zs2; zsize = g.zs2; }
+    const int nz = min(zsize, g.Do - z_first);
     if (IDENT) {
         if (threadIdx.y == 0 && threadIdx.x < nz) ident_z[threadIdx.x] = identity_coord(z_first + threadIdx.x + g.z_off, g.sp0);
         build_ident_table(ident, g, blockIdx.x * WARP_TX, blockIdx.y * (WARP_TY * WARP_VY), 0);
@@ -433,14 +461,14 @@ __global__ void __launch_bounds__(WARP_TX * WARP_TY, 4)   // 64 registers: measu
     const int a0 = z0a * g.HW + y0a * g.W + x0a, b0 = z0b * g.HW + y0b * g.W + x0b;      // signed: x0 may be -1
     const int a1 = a0 + g.W, a2 = a0 + g.HW, a3 = a2 + g.W;
     const int b1 = b0 + g.W, b2 = b0 + g.HW, b3 = b2 + g.W;
-    const f32x2 half = splat2(0.5f);
     f32x2 gix = splat2(0.0f), giy = splat2(0.0f), giz = splat2(0.0f);
 #pragma unroll 1
     for (int c = 0; c < g.C; ++c) {
         const float *sc = opaque(img_b + (int64_t)c * g.nvox);
         const float *goc = gout_b + (int64_t)c * g.nvox_o;
-        f32x2 go = pack2(ld_stream(goc + (unsigned)voxa), ld_stream(goc + (unsigned)voxb));
-        if (SCALE) go = mul2(go, splat2(2.0f));
+        // SCALE: d/dphi of 2*sample((img+1)/2) - 1.  The exact scalings by 2 (grad_out) and 1/2 (tap values) commute
+        // with every rounding below and cancel: use grad_out as it is and tap values img + 1.
+        const f32x2 go = pack2(ld_stream(goc + (unsigned)voxa), ld_stream(goc + (unsigned)voxb));
         const float *pa0 = sc + a0, *pa1 = sc + a1, *pa2 = sc + a2, *pa3 = sc + a3;
         const float *pb0 = sc + b0, *pb1 = sc + b1, *pb2 = sc + b2, *pb3 = sc + b3;
         f32x2 v[8];     // tap index t = tx + 2 ty + 4 tz
@@ -452,7 +480,7 @@ __global__ void __launch_bounds__(WARP_TX * WARP_TY, 4)   // 64 registers: measu
 #undef LR_TAP
         if (SCALE) {
 #pragma unroll
-            for (int t = 0; t < 8; ++t) v[t] = mul2(add2(v[t], one), half);
+            for (int t = 0; t < 8; ++t) v[t] = add2(v[t], one);
         }
         // d/dx: sum over (ty,tz) of (v[1,ty,tz] - v[0,ty,tz]) * wy*wz * go, and likewise for y and z.  The pairwise
         // weight products are formed on the fly (keeping 12 more packed values live would cost occupancy).
@@ -516,6 +544,7 @@ static WarpDims make_dims(int C, int D, int H, int W, int z_begin = 0, int z_cou
     g.mx = (float)(W - 1); g.my = (float)(H - 1); g.mz = (float)(D - 1);
     g.sp0 = 1.0 / (double)(D - 1); g.sp1 = 1.0 / (double)(H - 1); g.sp2 = 1.0 / (double)(W - 1);
     g.zero = 0.0f;
+    g.zs0 = g.zs1 = g.zs2 = 1; g.zn0 = g.zblocks; g.zn1 = 0;
     return g;
 }
 
@@ -534,6 +563,35 @@ static int batch_chunk(int D) { return 65535 / D > 0 ? 65535 / D : 1; }
 static dim3 warp_grid(int nb, int D, int H, int W, int rows_per_thread = 1) {
     const int rows = WARP_TY * rows_per_thread;
     return dim3((unsigned)((W + WARP_TX - 1) / WARP_TX), (unsigned)((H + rows - 1) / rows), (unsigned)(D * nb));
+}
+
+// z-blocking of the forward kernel.  A block is long (a plane of a 32 x 16 tile costs ~1.8 us, the block set-up about
+// one plane), the kernel is latency-bound (throughput follows occupancy), and the grid is only a few waves: with equal
+// blocks the launch ends with every SM draining from 4 resident blocks to 0 over a whole block duration (~15 % of
+// the kernel at 160^3).  So the blocks taper: most planes go into long blocks (set-up amortised over 8 planes), the
+// last quarter into short ones that fill the tail.
+static void forward_z_blocking(WarpDims &g) {
+    static int f0 = -1, f1 = -1;        // percent of the planes in 8-plane / 4-plane blocks (the rest: 2-plane blocks)
+    if (f0 < 0) {
+        int a = 55, b = 27;
+        if (const char *e = getenv("LIFTREG_B200_WARP_TAPER")) sscanf(e, "%d,%d", &a, &b);   // kernel experiments
+        f1 = b; f0 = a;
+    }
+    const int Do = g.Do;
+    g.zs0 = WARP_NZ_MAX; g.zs1 = 4; g.zs2 = 2;
+    if (Do < 32) {
+        g.zs0 = g.zs1 = g.zs2 = WARP_NZ;
+        g.zn0 = (Do + WARP_NZ - 1) / WARP_NZ; g.zn1 = 0;
+        g.zblocks = g.zn0;
+    } else {
+        g.zn0 = (Do * f0 / 100) / g.zs0;
+        const int rest = Do - g.zn0 * g.zs0;
+        g.zn1 = f0 + f1 >= 100 ? (rest + g.zs1 - 1) / g.zs1 : (Do * f1 / 100) / g.zs1;
+        if (g.zn1 * g.zs1 > rest) g.zn1 = (rest + g.zs1 - 1) / g.zs1;
+        const int rest2 = rest - g.zn1 * g.zs1 > 0 ? rest - g.zn1 * g.zs1 : 0;
+        g.zblocks = g.zn0 + g.zn1 + (rest2 + g.zs2 - 1) / g.zs2;
+    }
+    g.z_magic = (unsigned)(((1ull << 32) + (unsigned)g.zblocks - 1) / (unsigned)g.zblocks);
 }
 
 template <int PAD, int MODE>
@@ -585,8 +643,7 @@ extern "C" int lr_warp_forward_slab(const float *img, const float *phi, int B, i
     if (int e = check_warp_args(B, C, D, H, W, padding, mode)) return e;
     if (int e = check_slab(D, z_begin, z_count)) return e;
     WarpDims g = make_dims(C, D, H, W, z_begin, z_count);
-    g.zblocks = (g.Do + WARP_NZ - 1) / WARP_NZ;
-    g.z_magic = (unsigned)(((1ull << 32) + (unsigned)g.zblocks - 1) / (unsigned)g.zblocks);
+    forward_z_blocking(g);
     cudaStream_t st = as_stream(stream);
     const bool sc = using_scale != 0, id = disp_plus_identity != 0;
     const int chunk = batch_chunk(g.zblocks);
