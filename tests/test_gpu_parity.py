@@ -627,3 +627,81 @@ def test_pca_decode_matches_torch_linear_and_is_differentiable(dev):
     g = cu(rs.standard_normal(ref.shape).astype(np.float32), dev)
     ref.backward(g); ours.backward(g)
     assert rel_l2(c2.grad.cpu().numpy(), c1.grad.cpu().numpy()) <= GRAD_TOL
+
+
+@pytest.mark.parametrize("B,K,N", [(1, 56, 3 * 11 * 13 * 7), (4, 56, 5000), (17, 8, 777), (3, 160, 2049), (2, 4, 1), (33, 60, 4097)])
+def test_pca_decode_backward_vs_float64(dev, B, K, N):
+    """d/dcoefs of model :102 (F.linear): grad_coefs = grad_out @ basis, the second full pass over the basis.
+    fp32 partial sums in a launch-dependent order: compared with the float64 product."""
+    from liftreg_b200 import _native, ops
+    rs = np.random.RandomState(52)
+    basis = (rs.standard_normal((N, K)) * 1e-2).astype(np.float32)
+    gout = rs.standard_normal((B, N)).astype(np.float32)
+    want = gout.astype(np.float64) @ basis.astype(np.float64)
+    gc = torch.zeros((B, K), device=dev)
+    d_gout, d_basis = cu(gout, dev), cu(basis, dev)          # keep the tensors alive across the raw-pointer call
+    _native.check(_native.lib().lr_pca_decode_backward(ops._ptr(d_gout), ops._ptr(d_basis), B, K, N, ops._ptr(gc), ops._stream()),
+                  "lr_pca_decode_backward")
+    torch.cuda.synchronize()
+    assert rel_l2(gc.cpu().numpy(), want) <= GRAD_TOL
+    # through autograd, accumulating into an existing .grad
+    coefs = cu(rs.standard_normal((B, K)).astype(np.float32), dev).requires_grad_(True)
+    ops.pca_decode(coefs, d_basis).backward(d_gout)
+    assert rel_l2(coefs.grad.cpu().numpy(), want) <= GRAD_TOL
+
+
+def test_pca_decode_backward_odd_k_uses_library_gemm(dev):
+    from liftreg_b200 import ops
+    rs = np.random.RandomState(53)
+    basis = cu((rs.standard_normal((300, 7)) * 1e-2).astype(np.float32), dev)
+    coefs = cu(rs.standard_normal((2, 7)).astype(np.float32), dev).requires_grad_(True)
+    g = cu(rs.standard_normal((2, 300)).astype(np.float32), dev)
+    ops.pca_decode(coefs, basis).backward(g)
+    assert rel_l2(coefs.grad.cpu().numpy(), (g.double() @ basis.double()).cpu().numpy()) <= GRAD_TOL
+
+
+# ------------------------------------------------------------------ BASELINE configs[2] / configs[4] shapes
+def test_cfg3_batch8_full_size_is_batch_independent(dev):
+    """configs[2]: the hot-path ops of the full forward at 160^3, batch 8 (4 views, 256^2 detector).  Every batch item
+    must equal the batch-1 result of the same item, bit for bit, and item 0 must match the reference golden subset."""
+    from liftreg_b200 import ops, synthetic
+    shape, det, B, P = (160, 160, 160), (256, 256), 8, 4
+    rs = np.random.RandomState(60)
+    poses = synthetic.wrapper_poses(60.0, P, shape[1]).astype(np.float32)
+    proj = torch.from_numpy(rs.uniform(-1, 1, (B, P) + det).astype(np.float32)).to(dev)
+    moving = torch.from_numpy(rs.uniform(-1, 1, (B, 1) + shape).astype(np.float32)).to(dev)
+    disp = torch.stack([torch.from_numpy(synthetic.smooth_displacement(shape, seed=s)) for s in range(B)]).to(dev)
+    x = torch.empty((B, 1 + P) + shape, device=dev)                      # the encoder's concat buffer (row f1)
+    x[:, :1] = moving
+    ops.backproject(proj, poses, shape, out=x, channel_offset=1)
+    warped = ops.warp(moving, disp, zero_boundary=True, using_scale=True, disp_plus_identity=True)
+    for b in (0, 3, 7):
+        assert torch.equal(x[b, 1:], ops.backproject(proj[b:b + 1], poses, shape)[0])
+        assert torch.equal(warped[b:b + 1], ops.warp(moving[b:b + 1], disp[b:b + 1], zero_boundary=True, using_scale=True,
+                                                     disp_plus_identity=True))
+    assert torch.equal(x[:, 0], moving[:, 0])
+
+
+def test_cfg5_training_step_ops_batch4_forward_backward(dev):
+    """configs[4] (per-GPU share of batch 32 on 8 GPUs = 4 items): warp forward + d/dphi and the PCA decode adjoint at
+    160^3; gradients against the stock torch CUDA ops on the same device."""
+    import torch.nn.functional as F
+    from liftreg_b200 import net_utils, ops, synthetic
+    shape, B = (160, 160, 160), 4
+    rs = np.random.RandomState(61)
+    moving = torch.from_numpy(rs.uniform(-1, 1, (B, 1) + shape).astype(np.float32)).to(dev)
+    disp0 = torch.stack([torch.from_numpy(synthetic.smooth_displacement(shape, seed=10 + s)) for s in range(B)]).to(dev)
+    ident = net_utils.gen_identity_map(shape, 1.0)
+    gout = torch.from_numpy(rs.standard_normal((B, 1) + shape).astype(np.float32)).to(dev)
+
+    d1 = disp0.clone().requires_grad_(True)
+    ours = ops.warp(moving, d1, zero_boundary=True, using_scale=True, disp_plus_identity=True)
+    ours.backward(gout)
+    d2 = disp0.clone().requires_grad_(True)
+    phi = d2 + ident
+    grid = torch.stack([phi[:, 2], phi[:, 1], phi[:, 0]], dim=-1)        # net_utils.py:27-30
+    ref = F.grid_sample((moving + 1) / 2, grid, mode="bilinear", padding_mode="zeros", align_corners=True) * 2 - 1
+    ref.backward(gout)
+    for b in range(B):
+        assert rel_l2(ours[b].detach().cpu().numpy(), ref[b].detach().cpu().numpy()) <= TOL
+        assert rel_l2(d1.grad[b].cpu().numpy(), d2.grad[b].cpu().numpy()) <= GRAD_TOL
