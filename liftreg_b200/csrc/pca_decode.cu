@@ -265,7 +265,8 @@ static int launch_pca(const float *coefs, const float *basis, const float *mean,
                       cudaStream_t st) {
     const bool vec = g.K % 4 == 0 && ((uintptr_t)basis & 15) == 0;
     const int pitch = vec ? pd_pitch(g.K) : (g.K | 1);
-    const size_t smem = sizeof(float) * ((size_t)PD_ROWS * pitch + (size_t)g.K * BT);
+    // + 4 floats: the compiler reads the coefficient table four at a time in the k-loop's remainder iterations
+    const size_t smem = sizeof(float) * ((size_t)PD_ROWS * pitch + (size_t)g.K * BT + 4);
     if (smem > 200 * 1024) { set_error("pca_decode: K=%d needs %zu bytes of shared memory", g.K, smem); return LR_ERR_BAD_ARGUMENT; }
     if (smem > 48 * 1024) {       // opt in to large dynamic shared memory (idempotent, cheap)
         cudaError_t e = vec ? cudaFuncSetAttribute(pca_decode_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)
