@@ -13,8 +13,8 @@
 //
 // Work decomposition: the v-part of the map depends on (p,j,k), the u-part on (p,i,j).  A thread owns one k
 // (lanes along h: coalesced 128 B stores, near-contiguous gathers), keeps its v-part in registers and walks a
-// chunk of i; the per-i u-part comes from a small shared-memory table built once per block.  The batch loop is
-// innermost, so geometry and weights are shared by all B items.
+// chunk of i; the per-i u-part comes from a small shared-memory table built once per block and row j.  Batch items
+// are a grid dimension.
 #include <cstdio>
 #include <cstdlib>
 
@@ -43,7 +43,7 @@ struct BpDims {
     // index order, so the last ones to start are the short ones and the tail of the launch drains quickly):
     // nj0 runs of js0 rows, then nj1 of js1, then nj2 of js2, each for every (view, chunk)
     int js0, js1, js2, nj0, nj1, nj2;
-    int n_chunks, n_vc;            // forward: chunks of planes; views * chunks
+    int n_chunks, n_vc, n_views;   // forward: chunks of planes; batch items * views * chunks; views of this launch
     int p0;                        // first view of this launch
     float half_d, half_h;          // d/2, h/2 (exact)
     ConstDiv div_pw, div_ph;       // division by (float)pw, (float)ph via Markstein (bit-identical to IEEE division)
@@ -157,17 +157,20 @@ __global__ void __launch_bounds__(256)
     __shared__ float scale_all[2];
 
     const int tid = threadIdx.y * blockDim.x + threadIdx.x, n_thr = blockDim.x * blockDim.y;
-    // block index -> (run of rows, chunk, view): level-major, then (view, chunk), the run fastest (neighbouring blocks
-    // gather from neighbouring detector patches)
+    // block index -> (run of rows, chunk, view, batch item): level-major (all long runs of the whole launch first, the
+    // single rows last), then (item, view, chunk), the run fastest (neighbouring blocks gather from neighbouring
+    // detector patches)
     int L = blockIdx.x, nj = g.nj0, js = g.js0, j_base = 0;
     if (L >= g.nj0 * g.n_vc) {
         L -= g.nj0 * g.n_vc; nj = g.nj1; js = g.js1; j_base = g.nj0 * g.js0;
         if (L >= g.nj1 * g.n_vc) { L -= g.nj1 * g.n_vc; nj = g.nj2; js = g.js2; j_base += g.nj1 * g.js1; }
     }
     const int vc = L / nj;
-    const int pl = vc / g.n_chunks;      // view inside this launch
+    const int bv = vc / g.n_chunks;
+    const int bi = bv / g.n_views;       // batch item
+    const int pl = bv - bi * g.n_views;  // view inside this launch
     const int p = g.p0 + pl;
-    const int i_begin = (vc - pl * g.n_chunks) * g.ichunk;
+    const int i_begin = (vc - bv * g.n_chunks) * g.ichunk;
     const int i_count = min(g.ichunk, g.d - i_begin);
     const int j_begin = j_base + (L - vc * nj) * js, j_end = min(g.w, j_begin + js);
     const float sx = poses.s[pl][0], sy = poses.s[pl][1], sz = poses.s[pl][2];
@@ -175,8 +178,10 @@ __global__ void __launch_bounds__(256)
     const int64_t proj_batch = (int64_t)g.P * g.proj_view_stride;
     const int64_t plane_bytes = (int64_t)g.w * g.h * 4;
     const unsigned plane = (unsigned)(g.w * g.h);
-    const float *pv0 = proj + (int64_t)p * g.proj_view_stride;
-    float *ob0 = out + (int64_t)p * g.out_chan_stride + (int64_t)i_begin * g.w * g.h;
+    // batch items are blocks: a batch loop inside the thread (geometry shared by the items) made the blocks B times
+    // longer without adding any; at batch 8 that cost 27 us per item against 24 us for eight separate launches
+    const float *pv0 = proj + bi * proj_batch + (int64_t)p * g.proj_view_stride;
+    float *ob0 = out + bi * g.out_batch_stride + (int64_t)p * g.out_chan_stride + (int64_t)i_begin * g.w * g.h;
 
     for (int j = j_begin; j < j_end; ++j) {
         const int buf = (j - j_begin) & 1;
@@ -201,11 +206,9 @@ __global__ void __launch_bounds__(256)
             const float wq0 = t0.w1, e0 = sub_rn(1.0f, wq0), wq1 = t1.w1, e1 = sub_rn(1.0f, wq1);
             const bool c00 = (unsigned)t0.i0 < (unsigned)g.ph, c01 = (unsigned)(t0.i0 + 1) < (unsigned)g.ph;
             const bool c10 = (unsigned)t1.i0 < (unsigned)g.ph, c11 = (unsigned)(t1.i0 + 1) < (unsigned)g.ph;
-            // geometry (table + v-part) is shared by all batch items
-#pragma unroll 1
-            for (int b = 0; b < g.B; ++b) {
-                const float *pv = pv0 + b * proj_batch;
-                float *ob = ob0 + b * g.out_batch_stride + (unsigned)(j * g.h);
+            {
+                const float *pv = pv0;
+                float *ob = ob0 + (unsigned)(j * g.h);
                 if (rows_ok && has1 && c00 && c01 && c10 && c11) {
                     // every tap of every plane of this chunk is inside the detector (the common case).
                     // Sliding window over detector rows: the pair's two columns of rows r0, r0+1 stay in registers;
@@ -325,7 +328,7 @@ static int fill_dims(BpDims &g, int B, int P, int pw, int ph, int d_total, int w
     g.ichunk = (((d + n_chunks - 1) / n_chunks + 3) / 4) * 4;      // balanced, multiple of the unroll factor
     if (g.ichunk > BP_ICHUNK) g.ichunk = BP_ICHUNK;
     g.isub = g.ichunk; g.hp = (h + 1) / 2; g.bx = g.by = 1;
-    g.js0 = g.js1 = g.js2 = 1; g.nj0 = w; g.nj1 = g.nj2 = 0; g.n_chunks = g.n_vc = 1;
+    g.js0 = g.js1 = g.js2 = 1; g.nj0 = w; g.nj1 = g.nj2 = 0; g.n_chunks = g.n_vc = g.n_views = 1;
     g.half_d = (float)((double)d_total / 2.0); g.half_h = (float)((double)h / 2.0);
     g.div_pw = make_const_div((float)pw); g.div_ph = make_const_div((float)ph);
     g.hpw = (float)(pw - 1) / 2.0f; g.hph = (float)(ph - 1) / 2.0f;
@@ -351,11 +354,11 @@ static int block_threads(int h) {
 // equal blocks the launch ends with every SM draining from 6 resident blocks to 0 over a whole block duration.  The
 // runs therefore taper: 4 rows, then 2, then 1.
 static dim3 forward_shape(BpDims &g, int n_views, unsigned &grid) {
-    static int f0 = -1, f1 = -1;        // percent of the rows in 4-row / 2-row runs (the rest: single rows)
-    if (f0 < 0) {
-        int a = 50, b = 30;
+    static int f0_env = -1, f1_env = -1;   // LIFTREG_B200_BP_TAPER="f0,f1": percent of the rows in 4-row / 2-row runs
+    if (f0_env == -1) {
+        int a = -2, b = -2;
         if (const char *e = getenv("LIFTREG_B200_BP_TAPER")) sscanf(e, "%d,%d", &a, &b);   // kernel experiments
-        f1 = b; f0 = a;
+        f1_env = b; f0_env = a;
     }
     g.hp = (g.h + 1) / 2;
     g.bx = g.hp > 256 ? 256 : g.hp;
@@ -371,8 +374,19 @@ static dim3 forward_shape(BpDims &g, int n_views, unsigned &grid) {
     g.isub = isub;
     g.ichunk = isub * by;
     g.n_chunks = (g.d + g.ichunk - 1) / g.ichunk;
-    g.n_vc = g.n_chunks * n_views;
+    g.n_views = n_views;
+    g.n_vc = g.n_chunks * n_views * g.B;
     g.js0 = 4; g.js1 = 2; g.js2 = 1;
+    // share of the short runs: about 1.2 waves of work, at most half (measured: 50/30/20 % is best at batch 1 = 0.9
+    // waves of 4-row blocks on 6 resident blocks per SM, 90/8/2 % at batch 8)
+    int f0 = f0_env, f1 = f1_env;
+    if (f0 < 0) {
+        const double waves = (double)((g.w + g.js0 - 1) / g.js0) * g.n_vc / (6.0 * sm_count());
+        double small = 1.2 / (waves > 0.1 ? waves : 0.1);
+        if (small > 0.5) small = 0.5;
+        f0 = (int)(100.0 * (1.0 - small) + 0.5);
+        f1 = (int)(100.0 * 0.6 * small + 0.5);
+    }
     g.nj0 = (g.w * f0 / 100) / g.js0;
     int rest = g.w - g.nj0 * g.js0;
     g.nj1 = f0 + f1 >= 100 ? (rest + g.js1 - 1) / g.js1 : (g.w * f1 / 100) / g.js1;
@@ -402,6 +416,7 @@ extern "C" int lr_backproject_forward_slab(const float *proj, const float *poses
             for (int c = 0; c < 3; ++c) ps.s[q][c] = poses[(p0 + q) * 3 + c];
         g.p0 = p0;
         unsigned grid;
+        LR_REQUIRE((int64_t)w * ((d + 3) / 4) * np * B < (1ll << 31), "backproject_forward: too many blocks for one launch");
         const dim3 block = forward_shape(g, np, grid);
         backproject_forward_kernel<<<grid, block, 0, as_stream(stream)>>>(proj, out, g, ps);
         if (int e = check_launch("backproject_forward_kernel")) return e;

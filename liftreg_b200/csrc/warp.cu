@@ -566,16 +566,17 @@ static dim3 warp_grid(int nb, int D, int H, int W, int rows_per_thread = 1) {
 }
 
 // z-blocking of the forward kernel.  A block is long (a plane of a 32 x 16 tile costs ~1.8 us, the block set-up about
-// one plane), the kernel is latency-bound (throughput follows occupancy), and the grid is only a few waves: with equal
-// blocks the launch ends with every SM draining from 4 resident blocks to 0 over a whole block duration (~15 % of
-// the kernel at 160^3).  So the blocks taper: most planes go into long blocks (set-up amortised over 8 planes), the
-// last quarter into short ones that fill the tail.
-static void forward_z_blocking(WarpDims &g) {
-    static int f0 = -1, f1 = -1;        // percent of the planes in 8-plane / 4-plane blocks (the rest: 2-plane blocks)
-    if (f0 < 0) {
-        int a = 55, b = 27;
+// one plane), the kernel is latency-bound (throughput follows occupancy), and at batch 1 the grid is only a few waves:
+// with equal blocks the launch ends with every SM draining from 4 resident blocks to 0 over a whole block duration
+// (~15 % of the kernel at 160^3).  So the blocks taper: most planes go into 8-plane blocks (set-up amortised), the rest
+// into 4- and 2-plane blocks that are dispatched last (per batch item) and fill the tail.  The short blocks' share is about 1.2 waves of
+// work, at most 45 % (measured: 55/27/18 % is best at batch 1 = 1.7 waves, 100/0/0 at batch 8 = 13.5 waves).
+static void forward_z_blocking(WarpDims &g, int n_batch) {
+    static int f0_env = -1, f1_env = -1;        // LIFTREG_B200_WARP_TAPER="f0,f1": percent of the planes in 8- / 4-plane blocks
+    if (f0_env == -1) {
+        int a = -2, b = -2;
         if (const char *e = getenv("LIFTREG_B200_WARP_TAPER")) sscanf(e, "%d,%d", &a, &b);   // kernel experiments
-        f1 = b; f0 = a;
+        f1_env = b; f0_env = a;
     }
     const int Do = g.Do;
     g.zs0 = WARP_NZ_MAX; g.zs1 = 4; g.zs2 = 2;
@@ -584,6 +585,15 @@ static void forward_z_blocking(WarpDims &g) {
         g.zn0 = (Do + WARP_NZ - 1) / WARP_NZ; g.zn1 = 0;
         g.zblocks = g.zn0;
     } else {
+        int f0 = f0_env, f1 = f1_env;
+        if (f0 < 0) {
+            const double tiles = (double)((g.W + WARP_TX - 1) / WARP_TX) * ((g.H + WARP_TY * WARP_VY - 1) / (WARP_TY * WARP_VY));
+            const double waves = tiles * n_batch * ((Do + g.zs0 - 1) / g.zs0) / (4.0 * sm_count());
+            double small = 1.2 / (waves > 0.1 ? waves : 0.1);
+            if (small > 0.45) small = 0.45;
+            f0 = (int)(100.0 * (1.0 - small) + 0.5);
+            f1 = (int)(100.0 * 0.6 * small + 0.5);
+        }
         g.zn0 = (Do * f0 / 100) / g.zs0;
         const int rest = Do - g.zn0 * g.zs0;
         g.zn1 = f0 + f1 >= 100 ? (rest + g.zs1 - 1) / g.zs1 : (Do * f1 / 100) / g.zs1;
@@ -643,12 +653,12 @@ extern "C" int lr_warp_forward_slab(const float *img, const float *phi, int B, i
     if (int e = check_warp_args(B, C, D, H, W, padding, mode)) return e;
     if (int e = check_slab(D, z_begin, z_count)) return e;
     WarpDims g = make_dims(C, D, H, W, z_begin, z_count);
-    forward_z_blocking(g);
     cudaStream_t st = as_stream(stream);
     const bool sc = using_scale != 0, id = disp_plus_identity != 0;
-    const int chunk = batch_chunk(g.zblocks);
+    const int chunk = batch_chunk((g.Do + 1) / 2);          // upper bound of the z-blocks per item
     for (int b0 = 0; b0 < B; b0 += chunk) {
         const int nb = B - b0 < chunk ? B - b0 : chunk;
+        forward_z_blocking(g, nb);
         const dim3 grid = warp_grid(nb, g.zblocks, H, W, WARP_VY);
         const float *im = img + (int64_t)b0 * C * g.nvox, *ph = phi + (int64_t)b0 * 3 * g.nvox_o;
         float *o = out + (int64_t)b0 * C * g.nvox_o;

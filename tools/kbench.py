@@ -25,6 +25,11 @@ def main():
         k = args.index("--iters")
         iters = int(args[k + 1])
         del args[k:k + 2]
+    batch = 1
+    if "--batch" in args:        # batch items per launch for warp / backproject (BASELINE configs[2] uses 8)
+        k = args.index("--batch")
+        batch = int(args[k + 1])
+        del args[k:k + 2]
     which = args or ["warp", "backproject", "drr"]
     dev = torch.device("cuda:0")
     lib = _native.lib()
@@ -34,21 +39,21 @@ def main():
     vp = lambda t: ctypes.c_void_p(t.data_ptr())
     poses = synthetic.wrapper_poses(60.0, P, VOL[1])
     poses32 = np.ascontiguousarray(poses.astype(np.float32))
-    phi = torch.from_numpy((synthetic.smooth_displacement(VOL) + synthetic.identity_map_np(VOL))[None]).to(dev)
-    moving = torch.from_numpy(rs.uniform(-1, 1, (1, 1) + VOL).astype(np.float32)).to(dev)
-    proj = torch.from_numpy(rs.uniform(-1, 1, (1, P) + DET).astype(np.float32)).to(dev)
+    phi = torch.from_numpy((synthetic.smooth_displacement(VOL) + synthetic.identity_map_np(VOL))[None]).to(dev).repeat(batch, 1, 1, 1, 1)
+    moving = torch.from_numpy(rs.uniform(-1, 1, (1, 1) + VOL).astype(np.float32)).to(dev).repeat(batch, 1, 1, 1, 1)
+    proj = torch.from_numpy(rs.uniform(-1, 1, (1, P) + DET).astype(np.float32)).to(dev).repeat(batch, 1, 1, 1)
     mu = torch.from_numpy(rs.uniform(0, 0.3, (1,) + VOL).astype(np.float32)).to(dev)
     sets = [dict(phi=phi.clone(), moving=moving.clone(), proj=proj.clone(), mu=mu.clone(),
-                 warped=torch.empty((1, 1) + VOL, device=dev), lifted=torch.empty((1, P) + VOL, device=dev),
+                 warped=torch.empty((batch, 1) + VOL, device=dev), lifted=torch.empty((batch, P) + VOL, device=dev),
                  drr=torch.empty((1, P, 240, 240), device=dev)) for _ in range(R)]
     sp3 = np.array([2.2, 2.2, 2.2], np.float32)
     p64 = np.ascontiguousarray(poses, np.float64)
 
     def k_warp(s, st):
-        _native.check(lib.lr_warp_forward(vp(s["moving"]), vp(s["phi"]), 1, 1, *VOL, 0, 0, 1, 0, vp(s["warped"]), st), "warp")
+        _native.check(lib.lr_warp_forward(vp(s["moving"]), vp(s["phi"]), batch, 1, *VOL, 0, 0, 1, 0, vp(s["warped"]), st), "warp")
 
     def k_backproject(s, st):
-        _native.check(lib.lr_backproject_forward(vp(s["proj"]), ops._fp(poses32), 1, P, DET[0], DET[1], *VOL, vp(s["lifted"]),
+        _native.check(lib.lr_backproject_forward(vp(s["proj"]), ops._fp(poses32), batch, P, DET[0], DET[1], *VOL, vp(s["lifted"]),
                                                  P * nv, nv, st), "backproject")
 
     def k_drr(s, st):
@@ -88,9 +93,9 @@ def main():
     def k_pca(s, st):
         _native.check(lib.lr_pca_decode(vp(coefs), vp(basis), vp(pmean), 1, K, 3 * nv, 1, *VOL, vp(s["pout"]), st), "pca")
 
-    units = {"warp": (k_warp, nv, 20 * nv), "pca": (k_pca, 3 * nv, 4 * 3 * nv * 56 + 8 * 3 * nv),
+    units = {"warp": (k_warp, batch * nv, batch * 20 * nv), "pca": (k_pca, 3 * nv, 4 * 3 * nv * 56 + 8 * 3 * nv),
              "pca_bwd": (k_pca_bwd, 3 * nv, 4 * 3 * nv * 56 + 4 * 3 * nv), "warp_bwd": (k_warp_bwd, nv, 32 * nv),
-             "drr_bwd": (k_drr_bwd, P * 240 * 240 * VOL[1], 4 * nv + 4 * P * 240 * 240), "backproject": (k_backproject, P * nv, 4 * P * nv + 4 * P * DET[0] * DET[1]),
+             "drr_bwd": (k_drr_bwd, P * 240 * 240 * VOL[1], 4 * nv + 4 * P * 240 * 240), "backproject": (k_backproject, batch * P * nv, batch * (4 * P * nv + 4 * P * DET[0] * DET[1])),
              "drr": (k_drr, P * 240 * 240 * VOL[1], 4 * nv + 4 * P * 240 * 240)}
     for name in which:
         fn, n_units, nbytes = units[name]
