@@ -353,6 +353,43 @@ def run_b200(args):
                 "compulsory_bytes": comp_bytes, "gbps_compulsory": comp_bytes / us * 1e-3,
                 "gather_model_gbps": 16.0 * nominal / us * 1e-3}
 
+    # ---- the two streaming kernels at batch 8 (BASELINE configs[2]: the full forward runs them on 8 items per launch):
+    # same kernels, same entry points, 2 rotating buffer sets of 1.2 GB each; reported per launch and per item
+    batch8 = None
+    if rank == 0:
+        B8 = 8
+        b_proj = [torch.from_numpy(target_proj).to(dev).repeat(B8, 1, 1, 1) for _ in range(2)]
+        b_mov = [torch.from_numpy(moving).to(dev).repeat(B8, 1, 1, 1, 1) for _ in range(2)]
+        b_phi = [torch.from_numpy(phi).to(dev).repeat(B8, 1, 1, 1, 1) for _ in range(2)]
+        b_lift = [torch.empty((B8, P) + VOL, device=dev) for _ in range(2)]
+        b_warp = [torch.empty((B8, 1) + VOL, device=dev) for _ in range(2)]
+
+        def k8_bp(i, stx):
+            _native.check(lib.lr_backproject_forward(vp(b_proj[i]), pp, B8, P, DET[0], DET[1], VOL[0], VOL[1], VOL[2],
+                                                     vp(b_lift[i]), P * nv, nv, stx), "lr_backproject_forward")
+
+        def k8_warp(i, stx):
+            _native.check(lib.lr_warp_forward(vp(b_mov[i]), vp(b_phi[i]), B8, 1, VOL[0], VOL[1], VOL[2], 0, 0, 1, 0,
+                                              vp(b_warp[i]), stx), "lr_warp_forward")
+
+        batch8 = {}
+        for name, fn, nbytes, nunits in (("backproject_forward_kernel", k8_bp, B8 * bytes_bp, B8 * units_bp),
+                                         ("warp_forward_kernel", k8_warp, B8 * bytes_warp, B8 * units_warp)):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
+                stx = ctypes.c_void_p(stream.cuda_stream)
+                for i in range(4):
+                    fn(i % 2, stx)
+                e0.record(stream)
+                for i in range(200):
+                    fn(i % 2, stx)
+                e1.record(stream)
+            torch.cuda.synchronize()
+            us = 1e3 * e0.elapsed_time(e1) / 200
+            batch8[name] = {"us_per_launch": us, "us_per_item": us / B8, "bytes": nbytes, "gbps": nbytes / us * 1e-3,
+                            "units_per_s": nunits / us * 1e6}
+        del b_proj, b_mov, b_phi, b_lift, b_warp
+
     # ---- PCA-subspace decode (model :102): streams the 2.75 GB basis once
     pca_extra = None
     if rank == 0:
@@ -497,6 +534,7 @@ def run_b200(args):
             "drr_forward_cfg1": {k: dict(v, frac_of_hbm_peak_compulsory=v["gbps_compulsory"] / peak) for k, v in drr_extra.items()},
             "drr_calculate_projection_e2e_ms": drr_e2e_ms,
             "pca_decode": dict(pca_extra, frac_of_hbm_peak=pca_extra["gbps"] / peak) if pca_extra else None,
+            "batch8_cfg3": ({k: dict(v, frac_of_hbm_peak=v["gbps"] / peak) for k, v in batch8.items()} if batch8 else None),
             "sustained_ms_per_step": sustained_ms,
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": world * units / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
