@@ -13,6 +13,14 @@
 
 #include "common.cuh"
 
+// resident blocks per SM the two packed kernels are compiled for (register cap = 65536 / (256 * n))
+#ifndef LR_WARP_FWD_MINBLOCKS
+#define LR_WARP_FWD_MINBLOCKS 4
+#endif
+#ifndef LR_WARP_BWD_MINBLOCKS
+#define LR_WARP_BWD_MINBLOCKS 3
+#endif
+
 namespace lr {
 
 constexpr int WARP_TX = 32;   // threads along W (coalesced 128 B rows)
@@ -228,7 +236,7 @@ __device__ __forceinline__ void warp_pair(const float *__restrict__ src, float *
 // processed, so the HBM latency of the phi stream (the only compulsory traffic besides the store) is hidden behind a
 // whole plane of arithmetic instead of being exposed once per voxel.
 template <int PAD, int MODE, bool SCALE, bool IDENT, bool C1>
-__global__ void __launch_bounds__(WARP_TX * WARP_TY, 4)   // 64 registers: 4 resident blocks per SM
+__global__ void __launch_bounds__(WARP_TX * WARP_TY, LR_WARP_FWD_MINBLOCKS)   // 4: 64 registers, 4 resident blocks per SM
     warp_forward_kernel(const float *__restrict__ img, const float *__restrict__ phi, float *__restrict__ out, WarpDims g) {
     __shared__ IdentTable<WARP_TY * WARP_VY> ident;
     __shared__ float ident_z[WARP_NZ_MAX];
@@ -406,37 +414,13 @@ __device__ __forceinline__ void warp_bwd_phi_one(const float *__restrict__ gout_
     st_stream(gp + 2 * (int64_t)g.nvox_o + vox, mul_rn(g.hx, gix));
 }
 
-template <bool SCALE, bool IDENT>
-__global__ void __launch_bounds__(WARP_TX * WARP_TY, 4)   // 64 registers: measured 45.0 us vs 47.4 us unconstrained (76 regs)
-    warp_backward_phi_kernel(const float *__restrict__ gout, const float *__restrict__ img, const float *__restrict__ phi,
-                             float *__restrict__ gphi, WarpDims g) {
-    __shared__ IdentTable<WARP_TY * WARP_VY> ident;
-    const int x = blockIdx.x * WARP_TX + threadIdx.x;
-    const int ya = blockIdx.y * (WARP_TY * WARP_VY) + threadIdx.y;
-    const int b = g.zblocks == 1 ? (int)blockIdx.z : (int)__umulhi(blockIdx.z, g.z_magic);
-    const int z = blockIdx.z - b * g.Do;
-    if (IDENT) build_ident_table(ident, g, blockIdx.x * WARP_TX, blockIdx.y * (WARP_TY * WARP_VY), z + g.z_off);
-    if (x >= g.W || ya >= g.H) return;
-    const bool has_b = ya + WARP_TY < g.H;
-    const int yb = has_b ? ya + WARP_TY : ya;
-    const int voxa = z * g.HW + ya * g.W + x, voxb = z * g.HW + yb * g.W + x;
-
-    const float *p0 = opaque(phi + (int64_t)b * 3 * g.nvox_o);
-    const float *p1 = opaque(p0 + g.nvox_o);
-    const float *p2 = opaque(p1 + g.nvox_o);
-    f32x2 gz = pack2(ld_stream(p0 + (unsigned)voxa), ld_stream(p0 + (unsigned)voxb));
-    f32x2 gy = pack2(ld_stream(p1 + (unsigned)voxa), ld_stream(p1 + (unsigned)voxb));
-    f32x2 gx = pack2(ld_stream(p2 + (unsigned)voxa), ld_stream(p2 + (unsigned)voxb));
-    if (IDENT) {
-        gz = add2(gz, splat2(ident.z));
-        gy = add2(gy, pack2(ident.y[threadIdx.y], ident.y[has_b ? threadIdx.y + WARP_TY : threadIdx.y]));
-        gx = add2(gx, splat2(ident.x[threadIdx.x]));
-    }
+// One plane of d/dphi for the thread's two voxels; gz/gy/gx are the (identity-corrected) map values of (a, b).
+template <bool SCALE>
+__device__ __forceinline__ void warp_bwd_phi_pair(const float *__restrict__ gout_b, const float *__restrict__ img_b,
+                                                  float *__restrict__ gp, const WarpDims &g, f32x2 gx, f32x2 gy, f32x2 gz,
+                                                  int voxa, int voxb, bool has_b) {
     const f32x2 one = splat2(1.0f);
     const f32x2 ix = mul2(add2(gx, one), splat2(g.hx)), iy = mul2(add2(gy, one), splat2(g.hy)), iz = mul2(add2(gz, one), splat2(g.hz));
-    const float *gout_b = opaque(gout + (int64_t)b * g.C * g.nvox_o);
-    const float *img_b = opaque(img + (int64_t)b * g.C * g.nvox);
-    float *gp = opaque(gphi + (int64_t)b * 3 * g.nvox_o);
 
     f32x2 fx, fy, fz;
     int x0a, x0b, y0a, y0b, z0a, z0b;
@@ -508,6 +492,66 @@ __global__ void __launch_bounds__(WARP_TX * WARP_TY, 4)   // 64 registers: measu
     st_stream(gp + g.nvox_o + voxa, ra); if (has_b) st_stream(gp + g.nvox_o + voxb, rb);
     unpack2(mul2(splat2(g.hx), gix), ra, rb);
     st_stream(gp + 2 * (int64_t)g.nvox_o + voxa, ra); if (has_b) st_stream(gp + 2 * (int64_t)g.nvox_o + voxb, rb);
+}
+
+// Same block shape and tapered z-blocking as the forward kernel: a run of consecutive planes per block, the map
+// values of plane z+1 fetched into registers before plane z is evaluated.  (With one plane per block the map and
+// grad_out loads sat at the head of every block with nothing to hide them: ncu long-scoreboard 7.3 warps per issue.)
+template <bool SCALE, bool IDENT>
+__global__ void __launch_bounds__(WARP_TX * WARP_TY, LR_WARP_BWD_MINBLOCKS)
+    warp_backward_phi_kernel(const float *__restrict__ gout, const float *__restrict__ img, const float *__restrict__ phi,
+                             float *__restrict__ gphi, WarpDims g) {
+    __shared__ IdentTable<WARP_TY * WARP_VY> ident;
+    __shared__ float ident_z[WARP_NZ_MAX];
+    const int x = blockIdx.x * WARP_TX + threadIdx.x;
+    const int ya = blockIdx.y * (WARP_TY * WARP_VY) + threadIdx.y;
+    const int b = g.zblocks == 1 ? (int)blockIdx.z : (int)__umulhi(blockIdx.z, g.z_magic);
+    const int zb = blockIdx.z - b * g.zblocks;
+    int z_first, zsize;
+    if (zb < g.zn0) { z_first = zb * g.zs0; zsize = g.zs0; }
+    else if (zb < g.zn0 + g.zn1) { z_first = g.zn0 * g.zs0 + (zb - g.zn0) * g.zs1; zsize = g.zs1; }
+    else { z_first = g.zn0 * g.zs0 + g.zn1 * g.zs1 + (zb - g.zn0 - g.zn1) * g.zs2; zsize = g.zs2; }
+    const int nz = min(zsize, g.Do - z_first);
+    if (IDENT) {
+        if (threadIdx.y == 0 && threadIdx.x < nz) ident_z[threadIdx.x] = identity_coord(z_first + threadIdx.x + g.z_off, g.sp0);
+        build_ident_table(ident, g, blockIdx.x * WARP_TX, blockIdx.y * (WARP_TY * WARP_VY), 0);
+    }
+    if (x >= g.W || ya >= g.H) return;
+    const bool has_b = ya + WARP_TY < g.H;
+    const int yb = has_b ? ya + WARP_TY : ya;
+    int voxa = z_first * g.HW + ya * g.W + x, voxb = z_first * g.HW + yb * g.W + x;
+
+    const float *p0 = opaque(phi + (int64_t)b * 3 * g.nvox_o);
+    const float *p1 = opaque(p0 + g.nvox_o);
+    const float *p2 = opaque(p1 + g.nvox_o);
+    const float *gout_b = opaque(gout + (int64_t)b * g.C * g.nvox_o);
+    const float *img_b = opaque(img + (int64_t)b * g.C * g.nvox);
+    float *gp = opaque(gphi + (int64_t)b * 3 * g.nvox_o);
+    f32x2 idx = 0, idy = 0;
+    if (IDENT) {
+        idx = splat2(ident.x[threadIdx.x]);
+        idy = pack2(ident.y[threadIdx.y], ident.y[has_b ? threadIdx.y + WARP_TY : threadIdx.y]);
+    }
+    float cza = ld_stream(p0 + (unsigned)voxa), cya = ld_stream(p1 + (unsigned)voxa), cxa = ld_stream(p2 + (unsigned)voxa);
+    float czb = ld_stream(p0 + (unsigned)voxb), cyb = ld_stream(p1 + (unsigned)voxb), cxb = ld_stream(p2 + (unsigned)voxb);
+#pragma unroll 1
+    for (int zi = 0; zi < nz; ++zi) {
+        float nza = 0.f, nya = 0.f, nxa = 0.f, nzb = 0.f, nyb = 0.f, nxb = 0.f;
+        if (zi + 1 < nz) {   // prefetch the next plane's map values
+            const unsigned na = (unsigned)(voxa + g.HW), nb = (unsigned)(voxb + g.HW);
+            nza = ld_stream(p0 + na); nya = ld_stream(p1 + na); nxa = ld_stream(p2 + na);
+            nzb = ld_stream(p0 + nb); nyb = ld_stream(p1 + nb); nxb = ld_stream(p2 + nb);
+        }
+        f32x2 gx = pack2(cxa, cxb), gy = pack2(cya, cyb), gz = pack2(cza, czb);
+        if (IDENT) {
+            gz = add2(gz, splat2(ident_z[zi]));
+            gy = add2(gy, idy);
+            gx = add2(gx, idx);
+        }
+        warp_bwd_phi_pair<SCALE>(gout_b, img_b, gp, g, gx, gy, gz, voxa, voxb, has_b);
+        cza = nza; cya = nya; cxa = nxa; czb = nzb; cyb = nyb; cxb = nxb;
+        voxa += g.HW; voxb += g.HW;
+    }
 }
 
 __global__ void __launch_bounds__(WARP_TX * WARP_TY) identity_map_kernel(float *__restrict__ out, WarpDims g) {
@@ -706,14 +750,16 @@ extern "C" int lr_warp_backward_slab(const float *grad_out, const float *img, co
         float *gi = grad_img ? grad_img + io : nullptr, *gp = grad_phi ? grad_phi + po : nullptr;
         if (padding == LR_PAD_ZEROS && !gi) {
             // training configuration: map gradient only -> packed two-voxel kernel
-            const dim3 grid2 = warp_grid(nb, g.Do, H, W, WARP_VY);
+            WarpDims gz = g;                      // this kernel walks runs of planes (tapered z-blocks, as the forward)
+            forward_z_blocking(gz, nb);
+            const dim3 grid2 = warp_grid(nb, gz.zblocks, H, W, WARP_VY);
             const dim3 blk(WARP_TX, WARP_TY);
             if (sc) {
-                if (id) warp_backward_phi_kernel<true, true><<<grid2, blk, 0, st>>>(grad_out + oo, img + io, phi + po, gp, g);
-                else warp_backward_phi_kernel<true, false><<<grid2, blk, 0, st>>>(grad_out + oo, img + io, phi + po, gp, g);
+                if (id) warp_backward_phi_kernel<true, true><<<grid2, blk, 0, st>>>(grad_out + oo, img + io, phi + po, gp, gz);
+                else warp_backward_phi_kernel<true, false><<<grid2, blk, 0, st>>>(grad_out + oo, img + io, phi + po, gp, gz);
             } else {
-                if (id) warp_backward_phi_kernel<false, true><<<grid2, blk, 0, st>>>(grad_out + oo, img + io, phi + po, gp, g);
-                else warp_backward_phi_kernel<false, false><<<grid2, blk, 0, st>>>(grad_out + oo, img + io, phi + po, gp, g);
+                if (id) warp_backward_phi_kernel<false, true><<<grid2, blk, 0, st>>>(grad_out + oo, img + io, phi + po, gp, gz);
+                else warp_backward_phi_kernel<false, false><<<grid2, blk, 0, st>>>(grad_out + oo, img + io, phi + po, gp, gz);
             }
         } else if (padding == LR_PAD_ZEROS) launch_bwd<LR_PAD_ZEROS>(sc, id, grid, st, grad_out + oo, img + io, phi + po, gi, gp, g);
         else launch_bwd<LR_PAD_BORDER>(sc, id, grid, st, grad_out + oo, img + io, phi + po, gi, gp, g);
