@@ -200,6 +200,17 @@ LR_API int lr_pca_decode_backward(const float *grad_out, const float *basis, int
 /* replaces sdct:6-13 calc_relative_atten_coef(_cuda): mu = (max(HU,-1000)+1000)/1000*0.2; in place allowed */
 LR_API int lr_atten_coef(const float *hu, int64_t n, float *mu, lr_stream_t stream);
 
+/* ---- similarity loss on the warp output -------------- */
+/* replaces src/liftreg/layers/losses.py:14-29 NCCLoss.forward (training similarity, SubspaceLoss.py:27; validation score,
+ * RegistrationNet.py:210-212):  a = x - mean(x) + 1e-10, b = y - mean(y) + 1e-10 per batch item over N voxels,
+ * ncc = mean(a*b) / sqrt(mean(a*a) * mean(b*b)).
+ * lr_ncc_sums fills sums (B,7) float64, device memory owned by the caller (zeroed by the call):
+ *   [sum x, sum y, sum a*b, sum a*a, sum b*b, sum a, sum b]  ->  ncc_b = s2 / sqrt(s3*s4); loss = 1 - mean_b ncc_b.
+ * lr_ncc_backward: grad_x (B,N) = d(loss)/dx * grad_loss[0] (grad_loss: one float in device memory), from the same sums. */
+LR_API int lr_ncc_sums(const float *x, const float *y, int B, int64_t N, double *sums, lr_stream_t stream);
+LR_API int lr_ncc_backward(const float *x, const float *y, int B, int64_t N, const double *sums, const float *grad_loss,
+                           float *grad_x, lr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -350,3 +350,39 @@ def pca_decode(coefs, pca_vectors, pca_mean=None, img_shape=None, add_identity=F
     if img_shape is not None:
         return out.reshape(coefs.shape[0], 3, *[int(s) for s in img_shape])
     return out
+
+
+# --------------------------------------------------------------------------- NCC similarity (row f4)
+class _Ncc(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y):
+        x = _need_cuda_f32(x, "input")
+        y = _need_cuda_f32(y, "target")
+        B = x.shape[0]
+        N = x.numel() // B
+        sums = torch.empty((B, 7), device=x.device, dtype=torch.float64)
+        with torch.cuda.device(x.device):
+            _native.check(_native.lib().lr_ncc_sums(_ptr(x), _ptr(y), B, N, _ptr(sums), _stream()), "lr_ncc_sums")
+        ncc = sums[:, 2] / torch.sqrt(sums[:, 3] * sums[:, 4])           # the 1/N of the three means cancels
+        ctx.save_for_backward(x, y, sums)
+        return (1.0 - ncc.mean()).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        x, y, sums = ctx.saved_tensors
+        B = x.shape[0]
+        N = x.numel() // B
+        g = grad_loss.to(device=x.device, dtype=torch.float32).reshape(1).contiguous()
+        gx = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _native.check(_native.lib().lr_ncc_backward(_ptr(x), _ptr(y), B, N, _ptr(sums), _ptr(g), _ptr(gx), _stream()),
+                          "lr_ncc_backward")
+        return gx, None
+
+
+def ncc_loss(input, target):
+    """1 - mean over the batch of the normalised cross correlation -- reference layers/losses.py:14-29 (NCCLoss).
+    Differentiable wrt `input` (the warped image); `target` is data."""
+    if input.shape != target.shape:
+        raise ValueError("input %s and target %s must have the same shape" % (tuple(input.shape), tuple(target.shape)))
+    return _Ncc.apply(input, target)

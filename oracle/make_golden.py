@@ -204,9 +204,32 @@ def g_atten():
          mu_inplace=sdct.calc_relative_atten_coef_cuda(torch.from_numpy(hu.copy())).numpy())
 
 
+def g_ncc():
+    """layers/losses.py:14-29 NCCLoss (value and gradient wrt the input).  The module imports mermaid.finite_differences
+    at its top (not installable here, not used by NCCLoss): an empty stand-in module lets the import succeed."""
+    import types
+    for name in ("mermaid", "mermaid.finite_differences"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["mermaid"].finite_differences = sys.modules["mermaid.finite_differences"]
+    from liftreg.layers import losses as ref_losses
+    rs = np.random.RandomState(77)
+    shape = (3, 1, 12, 10, 14)
+    target = rs.uniform(-1, 1, shape).astype(np.float32)
+    warped = (0.7 * target + 0.3 * rs.uniform(-1, 1, shape)).astype(np.float32)
+    x = torch.from_numpy(warped).requires_grad_(True)
+    loss = ref_losses.NCCLoss()(x, torch.from_numpy(target))
+    loss.backward()
+    save("ncc", warped=warped, target=target, loss=loss.detach().numpy(), grad=x.grad.numpy())
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
+    if len(sys.argv) > 1:                      # regenerate selected fixtures only: python oracle/make_golden.py ncc ...
+        for name in sys.argv[1:]:
+            globals()["g_" + name]()
+        sys.exit(0)
+    g_ncc()
     g_ray_grid()
     g_drr()
     g_proj_layer()

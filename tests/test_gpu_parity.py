@@ -705,3 +705,56 @@ def test_cfg5_training_step_ops_batch4_forward_backward(dev):
     for b in range(B):
         assert rel_l2(ours[b].detach().cpu().numpy(), ref[b].detach().cpu().numpy()) <= TOL
         assert rel_l2(d1.grad[b].cpu().numpy(), d2.grad[b].cpu().numpy()) <= GRAD_TOL
+
+
+# ------------------------------------------------------------------ row f4: similarity loss and label warp
+def test_ncc_loss_vs_reference_golden(dev):
+    """NCCLoss mirror (two fused passes + one backward pass) against the reference's value and gradient; fp32 tolerance:
+    the reference sums in torch's fp32 cascade, the kernels in fp32 partials + fp64."""
+    from liftreg_b200 import losses
+    g = load_golden("ncc")
+    x = cu(g["warped"], dev).requires_grad_(True)
+    loss = losses.NCCLoss()(x, cu(g["target"], dev))
+    loss.backward()
+    assert abs(float(loss) - float(g["loss"])) <= 1e-6
+    assert rel_l2(x.grad.cpu().numpy(), g["grad"]) <= GRAD_TOL
+
+
+@pytest.mark.parametrize("B,shape", [(1, (160, 160, 160)), (4, (33, 20, 47)), (2, (1, 1, 3))])
+def test_ncc_loss_vs_torch_port(dev, B, shape):
+    from liftreg_b200 import ops
+    from oracle import torch_port
+    rs = np.random.RandomState(70)
+    target = rs.uniform(-1, 1, (B, 1) + shape).astype(np.float32)
+    warped = (0.6 * target + 0.4 * rs.uniform(-1, 1, (B, 1) + shape)).astype(np.float32)
+    x = cu(warped, dev).requires_grad_(True)
+    loss = ops.ncc_loss(x, cu(target, dev))
+    (3.0 * loss).backward()
+    xr = torch.from_numpy(warped).double().requires_grad_(True)            # float64 evaluation of the same formula
+    ref = torch_port.ncc_loss(xr, torch.from_numpy(target).double())
+    (3.0 * ref).backward()
+    assert abs(float(loss) - float(ref)) <= 2e-6
+    assert rel_l2(x.grad.cpu().numpy(), xr.grad.numpy()) <= GRAD_TOL
+
+
+def test_label_warp_mirror_of_mermaid_entry_point(dev):
+    """RegistrationNet.py:191-196: compute_warped_image_multiNC(labels, phi, spacing, spline_order=0, zero_boundary=True,
+    use_01_input=False) == nearest-mode spatial transformer without intensity rescaling (pinned nearest arithmetic)."""
+    from liftreg_b200 import mermaid_utils
+    from oracle import c_oracle
+    g = load_golden("warp_small")
+    img, phi = g["img"], g["phi"]
+    labels = (img > 0).astype(np.float32)
+    out = mermaid_utils.compute_warped_image_multiNC(cu(labels, dev), cu(phi, dev), (1.0, 1.0, 1.0), spline_order=0,
+                                                     zero_boundary=True, use_01_input=False)
+    assert np.array_equal(out.cpu().numpy(), c_oracle.warp_forward(labels, phi, True, False, "nearest"))
+    lin = mermaid_utils.compute_warped_image_multiNC(cu(img, dev), cu(phi, dev), (1.0, 1.0, 1.0), spline_order=1,
+                                                     zero_boundary=False, use_01_input=False)
+    assert np.array_equal(lin.cpu().numpy(), c_oracle.warp_forward(img, phi, False, False, "bilinear"))
+    # use_01_input: the map is given in [0, spacing*(sz-1)] and rescaled to [-1, 1] first
+    sz = np.array(phi.shape[2:], np.float64)
+    spacing = 1.0 / (sz - 1)
+    phi01 = ((phi.astype(np.float64) / 2 + 0.5) * (spacing * (sz - 1)).reshape(1, 3, 1, 1, 1)).astype(np.float32)
+    out01 = mermaid_utils.compute_warped_image_multiNC(cu(img, dev), cu(phi01, dev), spacing, spline_order=1,
+                                                       zero_boundary=False, use_01_input=True)
+    assert rel_l2(out01.cpu().numpy(), lin.cpu().numpy()) <= 1e-4       # coordinates round-trip through [0, 1] in fp32
