@@ -186,7 +186,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    _emit(line)
     return 0
 
 
@@ -546,13 +546,35 @@ def run_b200(args):
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
         }
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+_JSON_FD = None
+
+
+def _reserve_stdout():
+    """The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version line on the
+    first communicator when NCCL_DEBUG is set in the environment), so fd 1 is pointed at stderr for the whole run and
+    the JSON line goes to a private duplicate of the original stdout."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def _emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    _reserve_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)
