@@ -48,15 +48,24 @@ def _load_case(preprocessed_path, case_id, flip_axis1):
 
 
 def generate_drr_dataset(preprocessed_path, data_ids, drr_folder, scan_range=None, scan_num=None, geo_path=None,
-                         receptor_size=None, spacing=SPACING, flip_axis1=True, device="cuda", depth=3, project_fn=None):
+                         receptor_size=None, spacing=SPACING, flip_axis1=True, device="cuda", depth=3, project_fn=None,
+                         shard=None):
     """Writes `{id}_target_proj.npy`, `{id}_source_proj.npy` (float32 (P,rd,rh)) for every id and `poses.npy`
-    (float64 (P,3)) into `drr_folder`; returns the poses.  See the module docstring for the pipeline."""
+    (float64 (P,3)) into `drr_folder`; returns the poses.  See the module docstring for the pipeline.
+
+    shard=(rank, world): one process per GPU, each takes the cases rank, rank+world, ... (cases are independent: no
+    collective); rank 0 writes `poses.npy`."""
     data_ids = [str(d) for d in data_ids]
     os.makedirs(drr_folder, exist_ok=True)
     if not data_ids:
         return None
+    rank, world = (0, 1) if shard is None else (int(shard[0]), int(shard[1]))
+    if not 0 <= rank < world:
+        raise ValueError("shard=(rank, world) needs 0 <= rank < world, got %r" % (shard,))
+    first_id = data_ids[0]
+    data_ids = data_ids[rank::world]
     depth = max(1, int(depth))
-    first_t, _ = _load_case(preprocessed_path, data_ids[0], flip_axis1)
+    first_t, _ = _load_case(preprocessed_path, first_id, flip_axis1)
     shape = first_t.shape
     poses = dataset_poses(shape, scan_range, scan_num, geo_path, spacing)
     resolution = sdct._default_resolution(shape, receptor_size)
@@ -122,7 +131,8 @@ def generate_drr_dataset(preprocessed_path, data_ids, drr_folder, scan_range=Non
         t_load.join()
     if errors:
         raise errors[0]
-    np.save(os.path.join(drr_folder, "poses.npy"), poses)            # :154
+    if rank == 0:
+        np.save(os.path.join(drr_folder, "poses.npy"), poses)        # :154
     return poses
 
 

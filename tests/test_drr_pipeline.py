@@ -96,3 +96,27 @@ def test_pipeline_cuda_matches_serial_mirror_calls(tmp_path):
             got = np.load(os.path.join(out, "%s_%s_proj.npy" % (i, kind)))
             assert np.array_equal(got, ref)              # same kernel, same bits: batching and device-side HU->mu change nothing
             assert np.array_equal(poses, ref_poses)
+
+
+def test_pipeline_case_sharding_covers_every_case_once(tmp_path):
+    """shard=(rank, world): the ranks' case lists partition the ids, rank 0 alone writes poses.npy, and the union of
+    the files equals the unsharded run."""
+    shape = (8, 9, 7)
+    pre, out_a, out_b = str(tmp_path / "pre"), str(tmp_path / "a"), str(tmp_path / "b")
+    os.makedirs(pre)
+    ids = _make_dataset(pre, 5, shape)
+    kw = dict(scan_range=60.0, scan_num=2, receptor_size=(10, 11), project_fn=_oracle_project)
+    drr_pipeline.generate_drr_dataset(pre, ids, out_a, **kw)
+    drr_pipeline.generate_drr_dataset(pre, ids, out_b, shard=(1, 3), **kw)
+    assert sorted(os.listdir(out_b)) == sorted("%s_%s_proj.npy" % (i, k) for i in ids[1::3] for k in ("target", "source"))
+    drr_pipeline.generate_drr_dataset(pre, ids, out_b, shard=(0, 3), **kw)
+    drr_pipeline.generate_drr_dataset(pre, ids, out_b, shard=(2, 3), **kw)
+    assert sorted(os.listdir(out_a)) == sorted(os.listdir(out_b))
+    for f in os.listdir(out_a):
+        assert np.array_equal(np.load(os.path.join(out_a, f)), np.load(os.path.join(out_b, f)))
+    with pytest.raises(ValueError):
+        drr_pipeline.generate_drr_dataset(pre, ids, out_b, shard=(3, 3), **kw)
+    # more ranks than cases: the surplus rank writes nothing and does not fail
+    out_c = str(tmp_path / "c")
+    drr_pipeline.generate_drr_dataset(pre, ids[:1], out_c, shard=(1, 2), **kw)
+    assert os.listdir(out_c) == []

@@ -3,6 +3,7 @@
 
     python tools/preprocess_drr.py --preprocessed DATA/preprocessed --task-root DATA/task --out DATA/drr \
         [--phase all|train|debug|val|test] (--scan-range 60 --scan-num 4 | --geo-path geo.csv) [--receptor-size 256 256]
+    torchrun --nproc-per-node 8 --master-addr 127.0.0.1 tools/preprocess_drr.py ...      # cases sharded over the GPUs
 
 Reads `{task_root}/{phase}/data_id.npy` and `{preprocessed}/{id}_{target,source}.npy`, writes `{out}/drr/{id}_{target,source}_proj.npy`
 and `{out}/drr/poses.npy` exactly as the reference loop does (same names, shapes, dtypes and values); plotting previews is left to
@@ -38,6 +39,9 @@ def main():
     elif args.phase != "all":
         ap.error("Wrong phase value.")
     drr_folder = os.path.join(args.out, "drr")
+    # one process per GPU under torchrun: cases are split round-robin over the ranks (no collective)
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    device = args.device if world == 1 or ":" in args.device else "%s:%s" % (args.device, os.environ.get("LOCAL_RANK", "0"))
     poses = None
     for p in phases:
         ids_path = os.path.join(args.task_root, p, "data_id.npy")
@@ -48,7 +52,8 @@ def main():
         t0 = time.perf_counter()
         poses = drr_pipeline.generate_drr_dataset(args.preprocessed, ids, drr_folder, scan_range=args.scan_range,
                                                   scan_num=args.scan_num, geo_path=args.geo_path,
-                                                  receptor_size=args.receptor_size, device=args.device, depth=args.depth)
+                                                  receptor_size=args.receptor_size, device=device, depth=args.depth,
+                                                  shard=(rank, world))
         dt = time.perf_counter() - t0
         print("Processing data in %s ... %d cases in %.2f s (%.1f cases/s)" % (p, len(ids), dt, len(ids) / max(dt, 1e-9)))
     if poses is None:
