@@ -13,18 +13,21 @@
 
 #include "common.cuh"
 
-// resident blocks per SM the two packed kernels are compiled for (register cap = 65536 / (256 * n))
+// resident blocks per SM the two packed kernels are compiled for (register cap = 65536 / (32 * WARP_TY * n))
 #ifndef LR_WARP_FWD_MINBLOCKS
-#define LR_WARP_FWD_MINBLOCKS 4
+#define LR_WARP_FWD_MINBLOCKS 8      // 64 registers
 #endif
 #ifndef LR_WARP_BWD_MINBLOCKS
-#define LR_WARP_BWD_MINBLOCKS 3
+#define LR_WARP_BWD_MINBLOCKS 6      // 80 registers
 #endif
 
 namespace lr {
 
 constexpr int WARP_TX = 32;   // threads along W (coalesced 128 B rows)
-constexpr int WARP_TY = 8;    // thread rows per block
+#ifndef LR_WARP_TY
+#define LR_WARP_TY 4
+#endif
+constexpr int WARP_TY = LR_WARP_TY;    // thread rows per block (128-thread blocks: 23.1 us vs 23.9 us with 8 rows, 25.9 us with 16)
 constexpr int WARP_VY = 2;    // forward: output rows per thread (y and y + WARP_TY), processed as packed fp32x2
 constexpr int WARP_NZ = 4;    // forward: default consecutive planes per block (software-pipelined phi loads)
 constexpr int WARP_NZ_MAX = 8;   // forward: planes per block of the long blocks (see forward_z_blocking)
@@ -236,7 +239,7 @@ __device__ __forceinline__ void warp_pair(const float *__restrict__ src, float *
 // processed, so the HBM latency of the phi stream (the only compulsory traffic besides the store) is hidden behind a
 // whole plane of arithmetic instead of being exposed once per voxel.
 template <int PAD, int MODE, bool SCALE, bool IDENT, bool C1>
-__global__ void __launch_bounds__(WARP_TX * WARP_TY, LR_WARP_FWD_MINBLOCKS)   // 4: 64 registers, 4 resident blocks per SM
+__global__ void __launch_bounds__(WARP_TX * WARP_TY, LR_WARP_FWD_MINBLOCKS)   // 64 registers, 32 resident warps per SM
     warp_forward_kernel(const float *__restrict__ img, const float *__restrict__ phi, float *__restrict__ out, WarpDims g) {
     __shared__ IdentTable<WARP_TY * WARP_VY> ident;
     __shared__ float ident_z[WARP_NZ_MAX];
@@ -611,7 +614,7 @@ static dim3 warp_grid(int nb, int D, int H, int W, int rows_per_thread = 1) {
 
 // z-blocking of the forward kernel.  A block is long (a plane of a 32 x 16 tile costs ~1.8 us, the block set-up about
 // one plane), the kernel is latency-bound (throughput follows occupancy), and at batch 1 the grid is only a few waves:
-// with equal blocks the launch ends with every SM draining from 4 resident blocks to 0 over a whole block duration
+// with equal blocks the launch ends with every SM draining from full to empty over a whole block duration
 // (~15 % of the kernel at 160^3).  So the blocks taper: most planes go into 8-plane blocks (set-up amortised), the rest
 // into 4- and 2-plane blocks that are dispatched last (per batch item) and fill the tail.  The short blocks' share is about 1.2 waves of
 // work, at most 45 % (measured: 55/27/18 % is best at batch 1 = 1.7 waves, 100/0/0 at batch 8 = 13.5 waves).
@@ -632,7 +635,7 @@ static void forward_z_blocking(WarpDims &g, int n_batch) {
         int f0 = f0_env, f1 = f1_env;
         if (f0 < 0) {
             const double tiles = (double)((g.W + WARP_TX - 1) / WARP_TX) * ((g.H + WARP_TY * WARP_VY - 1) / (WARP_TY * WARP_VY));
-            const double waves = tiles * n_batch * ((Do + g.zs0 - 1) / g.zs0) / (4.0 * sm_count());
+            const double waves = tiles * n_batch * ((Do + g.zs0 - 1) / g.zs0) / (4.0 * sm_count());   // tuned with this count
             double small = 1.2 / (waves > 0.1 ? waves : 0.1);
             if (small > 0.45) small = 0.45;
             f0 = (int)(100.0 * (1.0 - small) + 0.5);
