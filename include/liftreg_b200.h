@@ -200,6 +200,13 @@ LR_API int lr_pca_decode_backward(const float *grad_out, const float *basis, int
 /* replaces sdct:6-13 calc_relative_atten_coef(_cuda): mu = (max(HU,-1000)+1000)/1000*0.2; in place allowed */
 LR_API int lr_atten_coef(const float *hu, int64_t n, float *mu, lr_stream_t stream);
 
+/* ---- launch plans (diagnostics for host-side tests; no device work) ------- */
+/* how lr_warp_forward cuts the z_count planes of an item into z-blocks: plan = {size0, n0, size1, n1, size2, n2} */
+LR_API int lr_warp_forward_plan(int B, int D, int H, int W, int z_count, int plan[6]);
+/* how lr_backproject_forward tiles planes, columns and rows: plan = {ichunk, isub, by, bx, n_chunks, run0, n0, run1, n1,
+ * run2, n2, grid} */
+LR_API int lr_backproject_forward_plan(int B, int P, int pw, int ph, int d, int w, int h, int plan[12]);
+
 /* ---- similarity loss on the warp output -------------- */
 /* replaces src/liftreg/layers/losses.py:14-29 NCCLoss.forward (training similarity, SubspaceLoss.py:27; validation score,
  * RegistrationNet.py:210-212):  a = x - mean(x) + 1e-10, b = y - mean(y) + 1e-10 per batch item over N voxels,

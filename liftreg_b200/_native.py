@@ -41,6 +41,8 @@ SIGNATURES = {
     "lr_pca_decode": (_i, [_vp, _vp, _vp, _i, _i, _i64, _i, _i, _i, _i, _vp, _vp]),
     "lr_pca_decode_backward": (_i, [_vp, _vp, _i, _i, _i64, _vp, _vp]),
     "lr_atten_coef": (_i, [_vp, _i64, _vp, _vp]),
+    "lr_warp_forward_plan": (_i, [_i, _i, _i, _i, _i, ctypes.POINTER(ctypes.c_int)]),
+    "lr_backproject_forward_plan": (_i, [_i, _i, _i, _i, _i, _i, _i, ctypes.POINTER(ctypes.c_int)]),
     "lr_ncc_sums": (_i, [_vp, _vp, _i, _i64, _vp, _vp]),
     "lr_ncc_backward": (_i, [_vp, _vp, _i, _i64, _vp, _vp, _vp, _vp]),
 }

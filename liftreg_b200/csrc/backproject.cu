@@ -424,6 +424,21 @@ extern "C" int lr_backproject_forward_slab(const float *proj, const float *poses
     return LR_OK;
 }
 
+// Launch plan of the forward kernel, for host-side tests (no device work).  plan = {ichunk, isub, by, bx, n_chunks,
+// run0, n0, run1, n1, run2, n2, grid}: chunks of ichunk planes (by sub-chunks of isub), bx column pairs per block;
+// the w rows are walked as n0 runs of run0 rows, then n1 of run1, then n2 of run2; grid blocks in total.
+extern "C" int lr_backproject_forward_plan(int B, int P, int pw, int ph, int d, int w, int h, int plan[12]) {
+    LR_REQUIRE(plan, "backproject_forward_plan: null pointer");
+    BpDims g;
+    if (int e = fill_dims(g, B, P, pw, ph, d, w, h, 0, 0)) return e;
+    unsigned grid = 0;
+    const int np = P < BP_MAX_VIEWS ? P : BP_MAX_VIEWS;
+    const dim3 block = forward_shape(g, np, grid);
+    plan[0] = g.ichunk; plan[1] = g.isub; plan[2] = (int)block.y; plan[3] = (int)block.x; plan[4] = g.n_chunks;
+    plan[5] = g.js0; plan[6] = g.nj0; plan[7] = g.js1; plan[8] = g.nj1; plan[9] = g.js2; plan[10] = g.nj2; plan[11] = (int)grid;
+    return LR_OK;
+}
+
 extern "C" int lr_backproject_forward(const float *proj, const float *poses, int B, int P, int pw, int ph, int d, int w,
                                       int h, float *out, int64_t out_batch_stride, int64_t out_chan_stride,
                                       lr_stream_t stream) {

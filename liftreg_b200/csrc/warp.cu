@@ -721,6 +721,20 @@ extern "C" int lr_warp_forward_slab(const float *img, const float *phi, int B, i
     return LR_OK;
 }
 
+// Launch plan of the forward kernel, for host-side tests (no device work): how the Do planes of an item are cut into
+// z-blocks.  plan = {size0, n0, size1, n1, size2, n2}: n0 blocks of size0 planes, then n1 of size1, then n2 of size2
+// (the last block may be partial).
+extern "C" int lr_warp_forward_plan(int B, int D, int H, int W, int z_count, int plan[6]) {
+    LR_REQUIRE(plan, "warp_forward_plan: null pointer");
+    if (int e = check_warp_args(B, 1, D, H, W, LR_PAD_ZEROS, LR_MODE_LINEAR)) return e;
+    if (int e = check_slab(D, 0, z_count)) return e;
+    WarpDims g = make_dims(1, D, H, W, 0, z_count);
+    const int chunk = batch_chunk((g.Do + 1) / 2);
+    forward_z_blocking(g, B < chunk ? B : chunk);
+    plan[0] = g.zs0; plan[1] = g.zn0; plan[2] = g.zs1; plan[3] = g.zn1; plan[4] = g.zs2; plan[5] = g.zblocks - g.zn0 - g.zn1;
+    return LR_OK;
+}
+
 extern "C" int lr_warp_forward(const float *img, const float *phi, int B, int C, int D, int H, int W, int padding,
                                int mode, int using_scale, int disp_plus_identity, float *out, lr_stream_t stream) {
     return lr_warp_forward_slab(img, phi, B, C, D, H, W, 0, D, padding, mode, using_scale, disp_plus_identity, out, stream);

@@ -154,3 +154,48 @@ def test_mirror_modules_expose_the_reference_surface():
     assert net_utils.Bilinear().zero_boundary == "border"
     a = np.array([[-1500.0, -1000.0, 0.0, 1000.0]], np.float32)
     assert np.allclose(sdct.calc_relative_atten_coef(a), [[0.0, 0.0, 0.2, 0.4]])
+
+
+# ------------------------------------------------------------------ launch plans (tapered block sizes) tile the work exactly
+def _plan(fn, n, *args):
+    import ctypes
+    from liftreg_b200 import _native
+    out = (ctypes.c_int * n)()
+    _native.check(getattr(_native.lib(), fn)(*args, out), fn)
+    return list(out)
+
+
+@pytest.mark.parametrize("B", [1, 2, 8, 64])
+def test_warp_forward_plan_tiles_every_plane_once(B):
+    """The z-blocks of lr_warp_forward (8-, 4- and 2-plane blocks, long ones first) must cover [0, Do) exactly once for
+    every slab height, whatever share the wave heuristic picks."""
+    for Do in list(range(1, 70)) + [96, 159, 160, 161, 255, 256, 320, 511, 512]:
+        for (H, W) in ((160, 160), (17, 33), (512, 512)):
+            s0, n0, s1, n1, s2, n2 = _plan("lr_warp_forward_plan", 6, B, max(Do, 2), H, W, Do)
+            assert min(s0, s1, s2) >= 1 and max(s0, s1, s2) <= 8 and min(n0, n1, n2) >= 0 and n0 + n1 + n2 >= 1
+            covered, z = np.zeros(Do, np.int32), 0
+            for size, n in ((s0, n0), (s1, n1), (s2, n2)):
+                for _ in range(n):
+                    assert z < Do, "a z-block starts beyond the slab (Do=%d B=%d H=%d W=%d)" % (Do, B, H, W)
+                    covered[z:min(Do, z + size)] += 1
+                    z += size
+            assert (covered == 1).all(), (Do, B, H, W, (s0, n0, s1, n1, s2, n2))
+
+
+@pytest.mark.parametrize("B", [1, 3, 8])
+def test_backproject_forward_plan_tiles_planes_and_rows_once(B):
+    """Chunks of planes x runs of rows of lr_backproject_forward: every (plane, row) belongs to exactly one block."""
+    for (d, w, h) in ((160, 160, 160), (1, 4, 1), (5, 7, 3), (33, 6, 70), (64, 65, 2), (320, 320, 320), (512, 512, 512), (31, 1, 600)):
+        for P in (1, 4, 64, 70):
+            ichunk, isub, by, bx, n_chunks, r0, n0, r1, n1, r2, n2, grid = _plan("lr_backproject_forward_plan", 12, B, P, 256, 256, d, w, h)
+            assert isub * by == ichunk and 1 <= ichunk <= 32 and isub % 4 == 0
+            assert (n_chunks - 1) * ichunk < d <= n_chunks * ichunk
+            assert 1 <= bx <= 256 and bx * by <= 256 and bx == min((h + 1) // 2, 256)
+            rows, j = np.zeros(w, np.int32), 0
+            for run, n in ((r0, n0), (r1, n1), (r2, n2)):
+                for _ in range(n):
+                    assert j < w
+                    rows[j:min(w, j + run)] += 1
+                    j += run
+            assert (rows == 1).all(), (d, w, h, P, B)
+            assert grid == (n0 + n1 + n2) * n_chunks * min(P, 64) * B
