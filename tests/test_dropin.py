@@ -44,3 +44,22 @@ print("OK", len(patched))
     env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1")
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
     assert res.returncode == 0 and "OK" in res.stdout, res.stdout + res.stderr
+
+
+def test_similarity_class_resolves_by_dotted_name_like_the_reference_does():
+    """losses/SubspaceLoss.py:12 instantiates the similarity through utils/general.py:9-15 get_class(dotted name); the
+    mirror must be reachable the same way (sim_class = 'liftreg_b200.losses.NCCLoss') and be an nn.Module."""
+    import torch.nn as nn
+
+    def get_class(kls):                    # the reference's lookup, restated: __import__ the module, walk the attributes
+        parts = kls.split('.')
+        m = __import__(".".join(parts[:-1]))
+        for comp in parts[1:]:
+            m = getattr(m, comp)
+        return m
+
+    sys.path.insert(0, ROOT)
+    cls = get_class("liftreg_b200.losses.NCCLoss")
+    assert isinstance(cls(), nn.Module) and callable(getattr(cls, "forward"))
+    from liftreg_b200 import mermaid_utils
+    assert callable(mermaid_utils.compute_warped_image_multiNC)

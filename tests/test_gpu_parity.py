@@ -716,7 +716,7 @@ def test_ncc_loss_vs_reference_golden(dev):
     x = cu(g["warped"], dev).requires_grad_(True)
     loss = losses.NCCLoss()(x, cu(g["target"], dev))
     loss.backward()
-    assert abs(float(loss) - float(g["loss"])) <= 1e-6
+    assert abs(loss.detach().item() - float(g["loss"])) <= 1e-6
     assert rel_l2(x.grad.cpu().numpy(), g["grad"]) <= GRAD_TOL
 
 
@@ -733,7 +733,7 @@ def test_ncc_loss_vs_torch_port(dev, B, shape):
     xr = torch.from_numpy(warped).double().requires_grad_(True)            # float64 evaluation of the same formula
     ref = torch_port.ncc_loss(xr, torch.from_numpy(target).double())
     (3.0 * ref).backward()
-    assert abs(float(loss) - float(ref)) <= 2e-6
+    assert abs(loss.detach().item() - ref.detach().item()) <= 2e-6
     assert rel_l2(x.grad.cpu().numpy(), xr.grad.numpy()) <= GRAD_TOL
 
 
