@@ -62,10 +62,21 @@ typedef enum {
 enum { LR_PAD_ZEROS = 0, LR_PAD_BORDER = 1 };     /* net_utils.py:21  zero_boundary ? zeros : border */
 enum { LR_MODE_LINEAR = 0, LR_MODE_NEAREST = 1 }; /* net_utils.py:23  mode = "bilinear" | "nearest"  */
 enum { LR_YNORM_WM1 = 0, LR_YNORM_W = 1 };        /* sdct:55 (/(w-1))  vs  layers.py:234 (/w)        */
+/* How the interpolation BLEND of lr_backproject_forward and lr_warp_forward (linear mode) is rounded.  Sample
+ * coordinates, floor indices and interpolation weights replay the reference's fp32 op chain bit for bit in both modes.
+ *   LR_NUMERICS_FAST  (default) the blend is a chain of fused linear interpolations (separable rows-then-columns for
+ *                     the backprojection, x-y-z lerps for the warp; `using_scale` folds away where all taps are inside):
+ *                     <= 1e-6 relative L2 from ATen's result (BASELINE.json's tolerance is 1e-5), half the instructions.
+ *   LR_NUMERICS_EXACT ATen's own operation order (grid_sampler_2d vector kernel / grid_sampler_3d scalar kernel):
+ *                     results bit-identical to the reference's torch CPU path.                                    */
+enum { LR_NUMERICS_FAST = 0, LR_NUMERICS_EXACT = 1 };
 
 /* ---- library ---------------------------------------------------------- */
 LR_API int lr_abi_version(void);
 LR_API const char *lr_last_error(void);
+/* process-wide numerics mode (also: environment LIFTREG_B200_NUMERICS=exact|fast read at first use) */
+LR_API int lr_set_numerics(int mode);
+LR_API int lr_get_numerics(void);
 /* number of CUDA devices visible, or a negative lr_status */
 LR_API int lr_device_count(void);
 /* kernels launched by this library (all threads) since the last reset (bench.py's gpu_launches) */

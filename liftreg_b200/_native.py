@@ -18,6 +18,8 @@ SIGNATURES = {
     "lr_abi_version": (_i, []),
     "lr_last_error": (ctypes.c_char_p, []),
     "lr_device_count": (_i, []),
+    "lr_set_numerics": (_i, [_i]),
+    "lr_get_numerics": (_i, []),
     "lr_launch_count": (ctypes.c_longlong, []),
     "lr_launch_count_reset": (None, []),
     "lr_drr_forward": (_i, [_vp, _i, _i, _i, _i, c_double_p, _i, _i, _i, _i, c_float_p, _i, _f, _vp, _vp]),
@@ -76,6 +78,21 @@ def check(status, what):
     if status != 0:
         msg = lib().lr_last_error()
         raise RuntimeError("%s failed (status %d): %s" % (what, status, msg.decode() if msg else "?"))
+
+
+NUMERICS = {"fast": 0, "exact": 1}
+
+
+def set_numerics(mode):
+    """'fast' (default: blends as fused lerps, <= 1e-6 rel-L2 from ATen) or 'exact' (ATen's operation order, bit-identical
+    values).  Indices and weights are bit-exact in both.  Returns the previous mode name."""
+    prev = get_numerics()
+    check(lib().lr_set_numerics(NUMERICS[mode] if isinstance(mode, str) else int(mode)), "lr_set_numerics")
+    return prev
+
+
+def get_numerics():
+    return "exact" if lib().lr_get_numerics() == 1 else "fast"
 
 
 def launch_count():

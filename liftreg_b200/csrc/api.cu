@@ -41,6 +41,18 @@ int sm_count() {
     return cached_n;
 }
 
+// Numerics of the interpolation blends (indices and weights are bit-exact in both modes): see lr_set_numerics.
+static std::atomic<int> g_numerics{-1};
+int numerics_mode() {
+    int m = g_numerics.load(std::memory_order_relaxed);
+    if (m < 0) {
+        const char *e = getenv("LIFTREG_B200_NUMERICS");
+        m = (e && (e[0] == 'e' || e[0] == 'E' || e[0] == '1')) ? LR_NUMERICS_EXACT : LR_NUMERICS_FAST;
+        g_numerics.store(m, std::memory_order_relaxed);
+    }
+    return m;
+}
+
 static size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
 
 // Pinned (page-locked, mapped) host memory can be read / written by kernels directly over PCIe (UVA).  The host
@@ -73,6 +85,13 @@ extern "C" int lr_abi_version(void) { return 1; }
 extern "C" const char *lr_last_error(void) { return g_err; }
 extern "C" long long lr_launch_count(void) { return g_launches.load(); }
 extern "C" void lr_launch_count_reset(void) { g_launches.store(0); }
+
+extern "C" int lr_set_numerics(int mode) {
+    LR_REQUIRE(mode == LR_NUMERICS_FAST || mode == LR_NUMERICS_EXACT, "set_numerics: mode must be 0 (fast) or 1 (exact)");
+    g_numerics.store(mode);
+    return LR_OK;
+}
+extern "C" int lr_get_numerics(void) { return numerics_mode(); }
 
 extern "C" int lr_device_count(void) {
     int n = 0;

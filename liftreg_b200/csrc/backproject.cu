@@ -50,6 +50,8 @@ struct BpDims {
     float hpw, hph;                // (pw-1)/2, (ph-1)/2
     int64_t proj_view_stride;      // pw*ph
     int64_t out_batch_stride, out_chan_stride;
+    float zero;                    // +0.0f the compiler cannot constant-fold (see mul2_sep)
+    int tma_out;                   // rows kernel: output rows leave through shared memory + cp.async.bulk (TMA)
 };
 
 struct AxisTap {      // one axis of the bilinear footprint
@@ -129,7 +131,15 @@ __device__ __forceinline__ float bilerp(float va, float vb, float vc, float vd, 
     return fma_rn(vd, se, fma_rn(vc, sw, fma_rn(vb, ne, mul_rn(va, nw))));
 }
 
+// The same four taps in the separable order of the fast-numerics kernel (see backproject_forward_rows_kernel):
+// the two detector rows are interpolated along the detector's second axis first, then blended along the first.
+__device__ __forceinline__ float bilerp_sep(float va, float vb, float vc, float vd, float s, float n, float e, float wq) {
+    const float t_lo = fma_rn(vb, wq, mul_rn(va, e)), t_up = fma_rn(vd, wq, mul_rn(vc, e));
+    return fma_rn(t_up, n, mul_rn(t_lo, s));
+}
+
 // Zeros-padding path of one voxel column (k): per-tap predicates, scalar arithmetic.
+template <bool SEP, bool TO_SMEM = false>
 __device__ __forceinline__ void backproject_column_checked(const float *pvf, char *o, int64_t plane_bytes, const BpRow *rows,
                                                            int ii0, int ii1, int ph, bool c0, bool c1, float e, float wq) {
     for (int ii = ii0; ii < ii1; ++ii) {
@@ -139,7 +149,9 @@ __device__ __forceinline__ void backproject_column_checked(const float *pvf, cha
         const bool rv0 = (r.mask & 1) != 0, rv1 = (r.mask & 2) != 0;
         const float va = (rv0 && c0) ? __ldg(q0) : 0.0f, vb = (rv0 && c1) ? __ldg(q0 + 1) : 0.0f;
         const float vc = (rv1 && c0) ? __ldg(q1) : 0.0f, vd = (rv1 && c1) ? __ldg(q1 + 1) : 0.0f;
-        st_stream((float *)o, bilerp(va, vb, vc, vd, r.s, r.n, e, wq));
+        const float res = SEP ? bilerp_sep(va, vb, vc, vd, r.s, r.n, e, wq) : bilerp(va, vb, vc, vd, r.s, r.n, e, wq);
+        if (TO_SMEM) *(float *)o = res;       // staging tile of the TMA variant (st.global cannot address shared memory)
+        else st_stream((float *)o, res);
         o += plane_bytes;
     }
 }
@@ -244,14 +256,238 @@ __global__ void __launch_bounds__(256)
                     }
                 } else {
                     // rays leaving the detector: per-tap predicates (zeros padding)
-                    backproject_column_checked(pv + t0.i0, (char *)(ob + k0) + ii0 * plane_bytes, plane_bytes, rows, ii0, ii1,
+                    backproject_column_checked<false>(pv + t0.i0, (char *)(ob + k0) + ii0 * plane_bytes, plane_bytes, rows, ii0, ii1,
                                                g.ph, c00, c01, e0, wq0);
                     if (has1)
-                        backproject_column_checked(pv + t1.i0, (char *)(ob + k1) + ii0 * plane_bytes, plane_bytes, rows, ii0,
+                        backproject_column_checked<false>(pv + t1.i0, (char *)(ob + k1) + ii0 * plane_bytes, plane_bytes, rows, ii0,
                                                    ii1, g.ph, c10, c11, e1, wq1);
                 }
             }
         }
+    }
+}
+
+// ---- forward, fast numerics: row-driven separable form ------------------------------------------------------------
+// Same decomposition, launch shape and index arithmetic as backproject_forward_kernel (floor indices and weights are
+// bit-identical: the same axis_tap chain), but the bilinear blend is evaluated separably,
+//     T[r][k]   = fma(P[r][c+1], wq, P[r][c] * e)             detector row r interpolated along the detector's 2nd axis
+//     out[i][k] = fma(T[r0+1][k], n, T[r0][k] * s)            rows r0(i), r0(i)+1 blended along the 1st axis
+// which differs from ATen's fma(se_v,n*w, fma(sw_v,n*e, fma(ne_v,s*w, nw_v*(s*e)))) by fp32 round-off only (tests: <= 1e-6
+// rel-L2; the oracle restates this order too and the kernel matches it bit for bit).  A thread marches over DETECTOR ROWS
+// instead of planes: consecutive planes move 1..1.4 rows down the detector (the magnification), so every row of the
+// chunk's range is fetched exactly once, its T computed once (2 packed ops for the thread's two columns) and blended
+// into the plane that ends at that row, if any (2 packed ops).  Per plane that is ~25 issue slots instead of ~38 for the
+// plane-driven window of the exact kernel (whose predicated-off row fetches still issue), and the per-row set-up is
+// half: warp 0 builds the chunk's tables with shuffles, everyone else only derives its two column taps (packed).
+//
+// Tables (double-buffered over the rows j a block walks):
+//   ev[slot]  slot = detector row - r_base.  n >= 0: the plane whose upper row this is, with row weight n; n < 0: none.
+//             roff = row * ph, or -1 when the row is outside the detector (its T is exactly +0: zeros padding).
+//   sub_lo/hi first (fetch only) and last slot of each sub-chunk of planes (one threadIdx.y slice).
+//   rows      the per-plane table of the generic path: taken by a (block, j) whose planes do not move strictly down the
+//             detector (magnification < 1, clamped far-outside coordinates) or span more than BP_EV_MAX rows.
+// With g.tma_out the block's output rows (h floats each, contiguous in HBM) are staged in shared memory and leave
+// through cp.async.bulk (TMA) instead of 128 B LSU stores: stores cost 2.8 L1 wavefronts per 128 B, a third of all.
+constexpr int BP_EV_MAX = 112;
+constexpr int BP_MAX_SUB = 8;
+static_assert(BP_ICHUNK <= 32, "warp 0 builds the chunk tables with one plane per lane");
+
+struct __align__(8) BpEvent {
+    float n;
+    int roff;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <bool CHK>
+__device__ __forceinline__ f32x2 bp_fetch_row(const float *lo0, const float *lo1, int roff, f32x2 e2, f32x2 w2, bool c00,
+                                              bool c01, bool c10, bool c11) {
+    f32x2 va, vb;
+    if (CHK) {
+        const bool rv = roff >= 0;
+        const unsigned o = rv ? (unsigned)roff : 0u;
+        const float *q0 = lo0 + o, *q1 = lo1 + o;
+        const float a0 = (rv && c00) ? __ldg(q0) : 0.0f, b0 = (rv && c01) ? __ldg(q0 + 1) : 0.0f;
+        const float a1 = (rv && c10) ? __ldg(q1) : 0.0f, b1 = (rv && c11) ? __ldg(q1 + 1) : 0.0f;
+        va = pack2(a0, a1); vb = pack2(b0, b1);
+    } else {
+        const float *q0 = lo0 + (unsigned)roff, *q1 = lo1 + (unsigned)roff;
+        va = pack2(__ldg(q0), __ldg(q1)); vb = pack2(__ldg(q0 + 1), __ldg(q1 + 1));
+    }
+    return fma2(vb, w2, mul2(va, e2));
+}
+
+// One thread's two columns over one sub-chunk of planes.  TMA: results go to the block's staging tile (row pitch h floats)
+template <bool CHK, bool TMA>
+__device__ __forceinline__ void bp_march_rows(const BpEvent *__restrict__ ev, int s_lo, int s_hi, const float *lo0,
+                                              const float *lo1, float *o0, float *o1, unsigned ofs, unsigned step,
+                                              f32x2 e2, f32x2 w2, bool c00, bool c01, bool c10, bool c11, bool has1) {
+    f32x2 t_prev = bp_fetch_row<CHK>(lo0, lo1, ev[s_lo].roff, e2, w2, c00, c01, c10, c11);
+#pragma unroll 4
+    for (int s = s_lo + 1; s <= s_hi; ++s) {
+        const BpEvent e = ev[s];
+        const f32x2 t = bp_fetch_row<CHK>(lo0, lo1, e.roff, e2, w2, c00, c01, c10, c11);
+        if (e.n >= 0.0f) {
+            const f32x2 n2 = splat2(e.n), s2 = splat2(sub_rn(1.0f, e.n));
+            float r0v, r1v;
+            unpack2(fma2(t, n2, mul2(t_prev, s2)), r0v, r1v);
+            if (TMA) {
+                o0[ofs] = r0v;
+                if (!CHK || has1) o1[ofs] = r1v;
+            } else {
+                st_stream(o0 + ofs, r0v);
+                if (!CHK || has1) st_stream(o1 + ofs, r1v);
+            }
+            ofs += step;
+        }
+        t_prev = t;
+    }
+}
+
+template <bool TMA>
+__global__ void __launch_bounds__(256)
+    backproject_forward_rows_kernel(const float *__restrict__ proj, float *__restrict__ out, BpDims g, BpPoses poses) {
+    __shared__ BpEvent ev_all[2][BP_EV_MAX];
+    __shared__ BpRow rows_all[2][BP_ICHUNK];
+    __shared__ int sub_lo[2][BP_MAX_SUB], sub_hi[2][BP_MAX_SUB];
+    __shared__ float scale_all[2];
+    __shared__ int flags_all[2];
+    extern __shared__ __align__(128) float stage[];      // TMA: [ichunk][h] output tile of the current row j
+
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    int L = blockIdx.x, nj = g.nj0, js = g.js0, j_base = 0;      // block index -> (run of rows, chunk, view, batch item)
+    if (L >= g.nj0 * g.n_vc) {
+        L -= g.nj0 * g.n_vc; nj = g.nj1; js = g.js1; j_base = g.nj0 * g.js0;
+        if (L >= g.nj1 * g.n_vc) { L -= g.nj1 * g.n_vc; nj = g.nj2; js = g.js2; j_base += g.nj1 * g.js1; }
+    }
+    const int vc = L / nj;
+    const int bv = vc / g.n_chunks;
+    const int bi = bv / g.n_views;
+    const int pl = bv - bi * g.n_views;
+    const int p = g.p0 + pl;
+    const int i_begin = (vc - bv * g.n_chunks) * g.ichunk;
+    const int i_count = min(g.ichunk, g.d - i_begin);
+    const int j_begin = j_base + (L - vc * nj) * js, j_end = min(g.w, j_begin + js);
+    const float sx = poses.s[pl][0], sy = poses.s[pl][1], sz = poses.s[pl][2];
+    const int ii0 = threadIdx.y * g.isub, ii1 = min(i_count, ii0 + g.isub);
+    const int64_t plane_bytes = (int64_t)g.w * g.h * 4;
+    const unsigned plane = (unsigned)(g.w * g.h);
+    const float *pv0 = proj + bi * ((int64_t)g.P * g.proj_view_stride) + (int64_t)p * g.proj_view_stride;
+    float *ob0 = out + bi * g.out_batch_stride + (int64_t)p * g.out_chan_stride + (int64_t)i_begin * g.w * g.h;
+    const f32x2 zero2 = splat2(g.zero);
+
+    for (int j = j_begin; j < j_end; ++j) {
+        const int buf = (j - j_begin) & 1;
+        if (tid < 32) {
+            // warp 0: one plane of the chunk per lane; neighbours' floor rows come by shuffle
+            const float scale = view_scale(sy, g.w, j);
+            const bool act = tid < i_count;
+            const AxisTap t = axis_tap((float)(g.i_off + i_begin + (act ? tid : 0)) - g.half_d, sx, scale, g.div_pw, g.hpw);
+            const int r0 = t.i0;
+            const int r_prev = __shfl_up_sync(0xffffffffu, r0, 1);
+            const int r_base = __shfl_sync(0xffffffffu, r0, 0);
+            const int r_last = __shfl_sync(0xffffffffu, r0, i_count - 1);
+            const bool mono = tid == 0 || !act || r0 > r_prev;
+            const bool fast = __all_sync(0xffffffffu, mono) && (r_last + 1 - r_base < BP_EV_MAX);
+            if (act) {
+                BpRow r;
+                r.off0 = r0 * g.ph; r.n = t.w1; r.s = sub_rn(1.0f, t.w1);
+                r.mask = ((unsigned)r0 < (unsigned)g.pw ? 1 : 0) | ((unsigned)(r0 + 1) < (unsigned)g.pw ? 2 : 0);
+                rows_all[buf][tid] = r;
+                if (fast) {
+                    BpEvent *ev = ev_all[buf];
+                    const int slot = r0 + 1 - r_base;
+                    for (int s = tid == 0 ? 0 : r_prev + 2 - r_base; s < slot; ++s) {      // rows no plane ends at
+                        const int r = r_base + s;
+                        BpEvent e; e.n = -1.0f; e.roff = (unsigned)r < (unsigned)g.pw ? r * g.ph : -1;
+                        ev[s] = e;
+                    }
+                    BpEvent e; e.n = t.w1; e.roff = (unsigned)(r0 + 1) < (unsigned)g.pw ? (r0 + 1) * g.ph : -1;
+                    ev[slot] = e;
+                    const int sub = tid / g.isub, rem = tid - sub * g.isub;
+                    if (rem == 0) sub_lo[buf][sub] = slot - 1;
+                    if (rem == g.isub - 1 || tid == i_count - 1) sub_hi[buf][sub] = slot;
+                }
+            }
+            if (tid == 0) {
+                scale_all[buf] = scale;
+                flags_all[buf] = (fast ? 1 : 0) | ((r_base >= 0 && r_last + 1 < g.pw) ? 2 : 0);
+            }
+        }
+        if (TMA) {
+            // the previous row's bulk copies must have read the staging tile before anyone overwrites it
+            if (tid < i_count) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        __syncthreads();
+        const int fl = flags_all[buf];
+        const float scale = scale_all[buf];
+        const BpRow *rows = rows_all[buf];
+
+        if (ii0 < ii1) {
+            for (int q = threadIdx.x; q < g.hp; q += blockDim.x) {
+                const int k0 = q, k1 = q + g.hp;
+                const bool has1 = k1 < g.h;
+                // both column taps as one packed chain (same op sequence as axis_tap)
+                const f32x2 cen = pack2((float)k0 - g.half_h, (float)(has1 ? k1 : k0) - g.half_h), sz2 = splat2(sz);
+                const f32x2 a = add2(mul2_sep(sub2(cen, sz2), splat2(scale), zero2), sz2);
+                const f32x2 gq = mul2(div_const2(a, g.div_ph), splat2(2.0f));
+                f32x2 ix = mul2(add2(gq, splat2(1.0f)), splat2(g.hph));
+                float ixa, ixb;
+                unpack2(ix, ixa, ixb);
+                const float hi = g.hph * 2.0f + 3.0f;
+                ix = pack2(clamp_index(ixa, hi), clamp_index(ixb, hi));
+                f32x2 fl2;
+                int c0, c1;
+                floor2_fi(ix, fl2, c0, c1);
+                const f32x2 w2 = sub2(ix, fl2), e2 = sub2(splat2(1.0f), w2);
+                const bool c00 = (unsigned)c0 < (unsigned)g.ph, c01 = (unsigned)(c0 + 1) < (unsigned)g.ph;
+                const bool c10 = has1 && (unsigned)c1 < (unsigned)g.ph, c11 = has1 && (unsigned)(c1 + 1) < (unsigned)g.ph;
+                float *ob = ob0 + (unsigned)(j * g.h);
+                if (fl & 1) {
+                    const int s_lo = sub_lo[buf][threadIdx.y], s_hi = sub_hi[buf][threadIdx.y];
+                    const float *lo0 = opaque(pv0 + c0), *lo1 = opaque(pv0 + c1);
+                    const bool interior = has1 && c00 && c01 && c10 && c11;
+                    const bool hot = (fl & 2) && __all_sync(__activemask(), interior);
+                    if (TMA) {
+                        float *o0 = stage + k0, *o1 = stage + k1;
+                        const unsigned ofs = (unsigned)(ii0 * g.h);
+                        if (hot) bp_march_rows<false, true>(ev_all[buf], s_lo, s_hi, lo0, lo1, o0, o1, ofs, (unsigned)g.h, e2, w2, c00, c01, c10, c11, has1);
+                        else bp_march_rows<true, true>(ev_all[buf], s_lo, s_hi, lo0, lo1, o0, o1, ofs, (unsigned)g.h, e2, w2, c00, c01, c10, c11, has1);
+                    } else {
+                        float *o0 = opaque(ob + k0), *o1 = opaque(ob + k1);
+                        const unsigned ofs = (unsigned)ii0 * plane;
+                        if (hot) bp_march_rows<false, false>(ev_all[buf], s_lo, s_hi, lo0, lo1, o0, o1, ofs, plane, e2, w2, c00, c01, c10, c11, has1);
+                        else bp_march_rows<true, false>(ev_all[buf], s_lo, s_hi, lo0, lo1, o0, o1, ofs, plane, e2, w2, c00, c01, c10, c11, has1);
+                    }
+                } else {
+                    // generic geometry: per-plane table, per-tap predicates, same separable blend
+                    float wq0, wq1, e0, e1;
+                    unpack2(w2, wq0, wq1); unpack2(e2, e0, e1);
+                    if (TMA) {
+                        backproject_column_checked<true, true>(pv0 + c0, (char *)(stage + k0) + ii0 * g.h * 4, (int64_t)g.h * 4, rows, ii0, ii1, g.ph, c00, c01, e0, wq0);
+                        if (has1) backproject_column_checked<true, true>(pv0 + c1, (char *)(stage + k1) + ii0 * g.h * 4, (int64_t)g.h * 4, rows, ii0, ii1, g.ph, c10, c11, e1, wq1);
+                    } else {
+                        backproject_column_checked<true>(pv0 + c0, (char *)(ob + k0) + ii0 * plane_bytes, plane_bytes, rows, ii0, ii1, g.ph, c00, c01, e0, wq0);
+                        if (has1) backproject_column_checked<true>(pv0 + c1, (char *)(ob + k1) + ii0 * plane_bytes, plane_bytes, rows, ii0, ii1, g.ph, c10, c11, e1, wq1);
+                    }
+                }
+            }
+        }
+        if (TMA) {
+            // staging tile complete -> one bulk copy per plane row (h*4 bytes, 16 B aligned: checked on the host)
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (tid < i_count) {
+                float *dst = ob0 + (unsigned)(j * g.h) + (unsigned)tid * plane;
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+                             "r"(smem_u32(stage + tid * g.h)), "r"(g.h * 4)
+                             : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
+    }
+    if (TMA) {
+        if (tid < i_count) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
 }
 
@@ -334,7 +570,17 @@ static int fill_dims(BpDims &g, int B, int P, int pw, int ph, int d_total, int w
     g.hpw = (float)(pw - 1) / 2.0f; g.hph = (float)(ph - 1) / 2.0f;
     g.proj_view_stride = (int64_t)pw * ph;
     g.out_batch_stride = obs; g.out_chan_stride = ocs;
+    g.zero = 0.0f; g.tma_out = 0;
     return LR_OK;
+}
+
+#ifndef LR_BP_TMA_DEFAULT
+#define LR_BP_TMA_DEFAULT 0
+#endif
+static bool bp_tma_enabled() {      // LIFTREG_B200_BP_TMA=0/1 (kernel experiments); default: see DESIGN.md section 5
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("LIFTREG_B200_BP_TMA"); v = e ? (e[0] == '1') : LR_BP_TMA_DEFAULT; }
+    return v != 0;
 }
 
 static int block_threads(int h) {
@@ -345,6 +591,7 @@ static int block_threads(int h) {
 #ifndef LR_BP_ISUB
 #define LR_BP_ISUB 16
 #endif
+
 #ifndef LR_BP_FWD_THREADS
 #define LR_BP_FWD_THREADS 192
 #endif
@@ -353,11 +600,12 @@ static int block_threads(int h) {
 // ~25 us launch, the kernel is latency-bound (throughput follows occupancy) and the grid is only a few waves, so with
 // equal blocks the launch ends with every SM draining from 6 resident blocks to 0 over a whole block duration.  The
 // runs therefore taper: 4 rows, then 2, then 1.
-static dim3 forward_shape(BpDims &g, int n_views, unsigned &grid) {
+static dim3 forward_shape(BpDims &g, int n_views, unsigned &grid, int min_threads = 1) {
     static int f0_env = -1, f1_env = -1;   // LIFTREG_B200_BP_TAPER="f0,f1": percent of the rows in 4-row / 2-row runs
     if (f0_env == -1) {
-        int a = -2, b = -2;
-        if (const char *e = getenv("LIFTREG_B200_BP_TAPER")) sscanf(e, "%d,%d", &a, &b);   // kernel experiments
+        int a = -2, b = -2;     // kernel experiments; anything that does not parse as two sane percentages is ignored
+        if (const char *e = getenv("LIFTREG_B200_BP_TAPER"))
+            if (sscanf(e, "%d,%d", &a, &b) != 2 || a < 0 || b < 0 || a + b > 100) a = b = -2;
         f1_env = b; f0_env = a;
     }
     g.hp = (g.h + 1) / 2;
@@ -370,6 +618,7 @@ static dim3 forward_shape(BpDims &g, int n_views, unsigned &grid) {
     const int n_chunks0 = (g.d + per_item - 1) / per_item;                    // balance the chunks over the planes
     isub = (((g.d + n_chunks0 - 1) / n_chunks0 + by - 1) / by + 3) / 4 * 4;   // multiple of the unroll factor
     if (isub > LR_BP_ISUB) isub = LR_BP_ISUB;
+    if (g.bx * by < min_threads) g.bx = (min_threads + by - 1) / by;     // tiny volumes: idle lanes, but a whole warp 0
     g.by = by;
     g.isub = isub;
     g.ichunk = isub * by;
@@ -417,9 +666,28 @@ extern "C" int lr_backproject_forward_slab(const float *proj, const float *poses
         g.p0 = p0;
         unsigned grid;
         LR_REQUIRE((int64_t)w * ((d + 3) / 4) * np * B < (1ll << 31), "backproject_forward: too many blocks for one launch");
-        const dim3 block = forward_shape(g, np, grid);
-        backproject_forward_kernel<<<grid, block, 0, as_stream(stream)>>>(proj, out, g, ps);
-        if (int e = check_launch("backproject_forward_kernel")) return e;
+        if (numerics_mode() == LR_NUMERICS_EXACT) {
+            const dim3 block = forward_shape(g, np, grid);
+            backproject_forward_kernel<<<grid, block, 0, as_stream(stream)>>>(proj, out, g, ps);
+            if (int e = check_launch("backproject_forward_kernel")) return e;
+            continue;
+        }
+        const dim3 block = forward_shape(g, np, grid, 32);
+        // output rows through shared memory + cp.async.bulk: needs 16-byte aligned rows everywhere
+        const size_t stage_bytes = sizeof(float) * (size_t)g.ichunk * h;
+        g.tma_out = bp_tma_enabled() && h % 4 == 0 && ((uintptr_t)out & 15) == 0 && out_batch_stride % 4 == 0 &&
+                    out_chan_stride % 4 == 0 && stage_bytes <= 96 * 1024;
+        if (g.tma_out) {
+            static thread_local size_t attr_set = 0;      // opt in above the 48 KB default once per thread / size
+            if (stage_bytes > 48 * 1024 && stage_bytes > attr_set) {
+                cudaFuncSetAttribute(backproject_forward_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+                attr_set = 96 * 1024;
+            }
+            backproject_forward_rows_kernel<true><<<grid, block, stage_bytes, as_stream(stream)>>>(proj, out, g, ps);
+        } else {
+            backproject_forward_rows_kernel<false><<<grid, block, 0, as_stream(stream)>>>(proj, out, g, ps);
+        }
+        if (int e = check_launch("backproject_forward_rows_kernel")) return e;
     }
     return LR_OK;
 }
@@ -433,7 +701,7 @@ extern "C" int lr_backproject_forward_plan(int B, int P, int pw, int ph, int d, 
     if (int e = fill_dims(g, B, P, pw, ph, d, w, h, 0, 0)) return e;
     unsigned grid = 0;
     const int np = P < BP_MAX_VIEWS ? P : BP_MAX_VIEWS;
-    const dim3 block = forward_shape(g, np, grid);
+    const dim3 block = forward_shape(g, np, grid, numerics_mode() == LR_NUMERICS_EXACT ? 1 : 32);
     plan[0] = g.ichunk; plan[1] = g.isub; plan[2] = (int)block.y; plan[3] = (int)block.x; plan[4] = g.n_chunks;
     plan[5] = g.js0; plan[6] = g.nj0; plan[7] = g.js1; plan[8] = g.nj1; plan[9] = g.js2; plan[10] = g.nj2; plan[11] = (int)grid;
     return LR_OK;

@@ -153,6 +153,7 @@ namespace lr {
 void set_error(const char *fmt, ...);
 int check_launch(const char *what);  // cudaGetLastError -> lr_status; bumps the per-thread launch counter
 int sm_count();                      // multiprocessors of the current device (cached per device)
+int numerics_mode();                 // LR_NUMERICS_FAST / LR_NUMERICS_EXACT (lr_set_numerics)
 inline cudaStream_t as_stream(lr_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 }  // namespace lr
 

@@ -234,11 +234,116 @@ __device__ __forceinline__ void warp_pair(const float *__restrict__ src, float *
     if (has_b) warp_one<PAD, MODE, SCALE>(src, dst + voxb, g, nchan, ixb, iyb, izb);
 }
 
+// ---- fast numerics (lr_set_numerics(LR_NUMERICS_FAST), linear mode) ---------------------------------------------------
+// Coordinates, floors and the three fractional weights are the same bit-exact chain as above; the 8-tap blend is
+// evaluated as seven fused linear interpolations,
+//     x:  c = fma(wx1, v(x0+1) - v(x0), v(x0))   (4x)      y:  fma(wy1, c(y0+1) - c(y0), c(y0))   (2x)      z: likewise (1x)
+// instead of ATen's 8 separately rounded (value * weight) products and 7 sums over 12 weight products.  `using_scale`
+// (sample (img+1)/2, return 2*out-1, net_utils.py:48-52) cancels exactly in real arithmetic because the weights sum to 1:
+// the taps are blended as they are, and a tap that zeros padding skips (intensity 0 after the rescaling) enters as -1.
+// 14 packed blend operations per voxel pair instead of 24 + 14 weight products + 2; <= 1e-6 rel-L2 from the exact mode.
+template <int PAD, bool SCALE>
+__device__ __forceinline__ void warp_one_fast(const float *__restrict__ src, float *__restrict__ dst, const WarpDims &g,
+                                              int nchan, float ix, float iy, float iz) {
+    if (PAD == LR_PAD_ZEROS) {
+        ix = clamp_index(ix, g.mx + 2.0f); iy = clamp_index(iy, g.my + 2.0f); iz = clamp_index(iz, g.mz + 2.0f);
+    }
+    float fx, fy, fz;
+    int x0, y0, z0;
+    floor_fi(ix, fx, x0);
+    floor_fi(iy, fy, y0);
+    floor_fi(iz, fz, z0);
+    const float wx1 = sub_rn(ix, fx), wy1 = sub_rn(iy, fy), wz1 = sub_rn(iz, fz);
+    const int base = z0 * g.HW + y0 * g.W + x0;
+    const bool vx0 = (unsigned)x0 < (unsigned)g.W, vx1 = (unsigned)(x0 + 1) < (unsigned)g.W;
+    const bool vy0 = (unsigned)y0 < (unsigned)g.H, vy1 = (unsigned)(y0 + 1) < (unsigned)g.H;
+    const bool vz0 = (unsigned)z0 < (unsigned)g.D, vz1 = (unsigned)(z0 + 1) < (unsigned)g.D;
+    const bool ok[8] = {vx0 && vy0 && vz0, vx1 && vy0 && vz0, vx0 && vy1 && vz0, vx1 && vy1 && vz0,
+                        vx0 && vy0 && vz1, vx1 && vy0 && vz1, vx0 && vy1 && vz1, vx1 && vy1 && vz1};
+    const int off[8] = {0, 1, g.W, g.W + 1, g.HW, g.HW + 1, g.HW + g.W, g.HW + g.W + 1};
+    const float masked = SCALE ? -1.0f : 0.0f;
+#pragma unroll 1
+    for (int c = 0; c < nchan; ++c) {
+        const float *s = src + (int64_t)c * g.nvox + base;
+        float v[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v[t] = ok[t] ? __ldg(s + off[t]) : masked;
+        const float c00 = fma_rn(wx1, sub_rn(v[1], v[0]), v[0]), c10 = fma_rn(wx1, sub_rn(v[3], v[2]), v[2]);
+        const float c01 = fma_rn(wx1, sub_rn(v[5], v[4]), v[4]), c11 = fma_rn(wx1, sub_rn(v[7], v[6]), v[6]);
+        const float d0 = fma_rn(wy1, sub_rn(c10, c00), c00), d1 = fma_rn(wy1, sub_rn(c11, c01), c01);
+        st_stream(dst + (int64_t)c * g.nvox_o, fma_rn(wz1, sub_rn(d1, d0), d0));
+    }
+}
+
+template <int PAD, bool SCALE>
+__device__ __forceinline__ void warp_pair_fast(const float *__restrict__ src, float *__restrict__ dst, const WarpDims &g,
+                                               int nchan, f32x2 gx, f32x2 gy, f32x2 gz, int voxa, int voxb, bool has_b) {
+    const f32x2 one = splat2(1.0f);
+    f32x2 ix = mul2(add2(gx, one), splat2(g.hx)), iy = mul2(add2(gy, one), splat2(g.hy)), iz = mul2(add2(gz, one), splat2(g.hz));
+    if (PAD == LR_PAD_BORDER) {   // clip_coordinates
+        float ixa, ixb, iya, iyb, iza, izb;
+        unpack2(ix, ixa, ixb); unpack2(iy, iya, iyb); unpack2(iz, iza, izb);
+        ixa = fminf(g.mx, fmaxf(ixa, 0.0f)); ixb = fminf(g.mx, fmaxf(ixb, 0.0f));
+        iya = fminf(g.my, fmaxf(iya, 0.0f)); iyb = fminf(g.my, fmaxf(iyb, 0.0f));
+        iza = fminf(g.mz, fmaxf(iza, 0.0f)); izb = fminf(g.mz, fmaxf(izb, 0.0f));
+        ix = pack2(ixa, ixb); iy = pack2(iya, iyb); iz = pack2(iza, izb);
+    }
+    f32x2 fx, fy, fz;
+    int x0a, x0b, y0a, y0b, z0a, z0b;
+    floor2_fi(ix, fx, x0a, x0b);
+    floor2_fi(iy, fy, y0a, y0b);
+    floor2_fi(iz, fz, z0a, z0b);
+    // packed path: both y/z tap pairs inside and at least one x tap inside (as warp_pair); NaN / far-out coordinates
+    // floor to indices outside any volume and take the scalar path
+    const bool ina = (unsigned)(x0a + 1) < (unsigned)(g.W + 1) && (unsigned)y0a < (unsigned)(g.H - 1) && (unsigned)z0a < (unsigned)(g.D - 1);
+    const bool inb = (unsigned)(x0b + 1) < (unsigned)(g.W + 1) && (unsigned)y0b < (unsigned)(g.H - 1) && (unsigned)z0b < (unsigned)(g.D - 1);
+    if (ina && inb) {
+        const f32x2 wx1 = sub2(ix, fx), wy1 = sub2(iy, fy), wz1 = sub2(iz, fz);
+        const bool la = x0a >= 0, ha = x0a < g.W - 1, lb = x0b >= 0, hb = x0b < g.W - 1;   // x taps inside?
+        const bool all_in = __all_sync(__activemask(), la && ha && lb && hb);
+        const int a0 = z0a * g.HW + y0a * g.W + x0a, b0 = z0b * g.HW + y0b * g.W + x0b;
+        const int a1 = a0 + g.W, a2 = a0 + g.HW, a3 = a2 + g.W;
+        const int b1 = b0 + g.W, b2 = b0 + g.HW, b3 = b2 + g.W;
+#pragma unroll 1
+        for (int c = 0; c < nchan; ++c) {
+            const float *sc = opaque(src + (int64_t)c * g.nvox);
+            const float *pa0 = sc + a0, *pa1 = sc + a1, *pa2 = sc + a2, *pa3 = sc + a3;
+            const float *pb0 = sc + b0, *pb1 = sc + b1, *pb2 = sc + b2, *pb3 = sc + b3;
+            f32x2 v[8];
+            if (all_in) {
+                v[0] = pack2(__ldg(pa0), __ldg(pb0)); v[1] = pack2(__ldg(pa0 + 1), __ldg(pb0 + 1));
+                v[2] = pack2(__ldg(pa1), __ldg(pb1)); v[3] = pack2(__ldg(pa1 + 1), __ldg(pb1 + 1));
+                v[4] = pack2(__ldg(pa2), __ldg(pb2)); v[5] = pack2(__ldg(pa2 + 1), __ldg(pb2 + 1));
+                v[6] = pack2(__ldg(pa3), __ldg(pb3)); v[7] = pack2(__ldg(pa3 + 1), __ldg(pb3 + 1));
+            } else {
+#define LR_TAP(p, ok) ((ok) ? __ldg(p) : (SCALE ? -1.0f : 0.0f))
+                v[0] = pack2(LR_TAP(pa0, la), LR_TAP(pb0, lb)); v[1] = pack2(LR_TAP(pa0 + 1, ha), LR_TAP(pb0 + 1, hb));
+                v[2] = pack2(LR_TAP(pa1, la), LR_TAP(pb1, lb)); v[3] = pack2(LR_TAP(pa1 + 1, ha), LR_TAP(pb1 + 1, hb));
+                v[4] = pack2(LR_TAP(pa2, la), LR_TAP(pb2, lb)); v[5] = pack2(LR_TAP(pa2 + 1, ha), LR_TAP(pb2 + 1, hb));
+                v[6] = pack2(LR_TAP(pa3, la), LR_TAP(pb3, lb)); v[7] = pack2(LR_TAP(pa3 + 1, ha), LR_TAP(pb3 + 1, hb));
+#undef LR_TAP
+            }
+            const f32x2 c00 = fma2(wx1, sub2(v[1], v[0]), v[0]), c10 = fma2(wx1, sub2(v[3], v[2]), v[2]);
+            const f32x2 c01 = fma2(wx1, sub2(v[5], v[4]), v[4]), c11 = fma2(wx1, sub2(v[7], v[6]), v[6]);
+            const f32x2 d0 = fma2(wy1, sub2(c10, c00), c00), d1 = fma2(wy1, sub2(c11, c01), c01);
+            float ra, rb;
+            unpack2(fma2(wz1, sub2(d1, d0), d0), ra, rb);
+            st_stream(dst + (int64_t)c * g.nvox_o + voxa, ra);
+            if (has_b) st_stream(dst + (int64_t)c * g.nvox_o + voxb, rb);
+        }
+        return;
+    }
+    float ixa, ixb, iya, iyb, iza, izb;
+    unpack2(ix, ixa, ixb); unpack2(iy, iya, iyb); unpack2(iz, iza, izb);
+    warp_one_fast<PAD, SCALE>(src, dst + voxa, g, nchan, ixa, iya, iza);
+    if (has_b) warp_one_fast<PAD, SCALE>(src, dst + voxb, g, nchan, ixb, iyb, izb);
+}
+
 // Forward kernel.  Thread (tx, ty) of block (bx, by, bz) owns output voxels (x, y, z) and (x, y + WARP_TY, z) for
 // a run of consecutive planes z (8, 4 or 2: forward_z_blocking).  The map values of plane z+1 are fetched into registers before plane z is
 // processed, so the HBM latency of the phi stream (the only compulsory traffic besides the store) is hidden behind a
 // whole plane of arithmetic instead of being exposed once per voxel.
-template <int PAD, int MODE, bool SCALE, bool IDENT, bool C1>
+template <int PAD, int MODE, bool SCALE, bool IDENT, bool C1, bool FAST>
 __global__ void __launch_bounds__(WARP_TX * WARP_TY, LR_WARP_FWD_MINBLOCKS)   // 64 registers, 32 resident warps per SM
     warp_forward_kernel(const float *__restrict__ img, const float *__restrict__ phi, float *__restrict__ out, WarpDims g) {
     __shared__ IdentTable<WARP_TY * WARP_VY> ident;
@@ -290,7 +395,8 @@ __global__ void __launch_bounds__(WARP_TX * WARP_TY, LR_WARP_FWD_MINBLOCKS)   //
             gy = add2(gy, idy);
             gx = add2(gx, idx);
         }
-        warp_pair<PAD, MODE, SCALE>(src, dst, g, nchan, gx, gy, gz, voxa, voxb, has_b);
+        if (FAST && MODE == LR_MODE_LINEAR) warp_pair_fast<PAD, SCALE>(src, dst, g, nchan, gx, gy, gz, voxa, voxb, has_b);
+        else warp_pair<PAD, MODE, SCALE>(src, dst, g, nchan, gx, gy, gz, voxa, voxb, has_b);
         cza = nza; cya = nya; cxa = nxa; czb = nzb; cyb = nyb; cxb = nxb;
         voxa += g.HW; voxb += g.HW;
     }
@@ -621,8 +727,9 @@ static dim3 warp_grid(int nb, int D, int H, int W, int rows_per_thread = 1) {
 static void forward_z_blocking(WarpDims &g, int n_batch) {
     static int f0_env = -1, f1_env = -1;        // LIFTREG_B200_WARP_TAPER="f0,f1": percent of the planes in 8- / 4-plane blocks
     if (f0_env == -1) {
-        int a = -2, b = -2;
-        if (const char *e = getenv("LIFTREG_B200_WARP_TAPER")) sscanf(e, "%d,%d", &a, &b);   // kernel experiments
+        int a = -2, b = -2;     // kernel experiments; anything that does not parse as two sane percentages is ignored
+        if (const char *e = getenv("LIFTREG_B200_WARP_TAPER"))
+            if (sscanf(e, "%d,%d", &a, &b) != 2 || a < 0 || b < 0 || a + b > 100) a = b = -2;
         f1_env = b; f0_env = a;
     }
     const int Do = g.Do;
@@ -655,10 +762,14 @@ template <int PAD, int MODE>
 static void launch_fwd(bool scale, bool ident, dim3 grid, cudaStream_t st, const float *img, const float *phi, float *out,
                        const WarpDims &g) {
     const dim3 blk(WARP_TX, WARP_TY);
-#define LR_LAUNCH_FWD(S, I)                                                                                  \
-    do {                                                                                                     \
-        if (g.C == 1) warp_forward_kernel<PAD, MODE, S, I, true><<<grid, blk, 0, st>>>(img, phi, out, g);     \
-        else warp_forward_kernel<PAD, MODE, S, I, false><<<grid, blk, 0, st>>>(img, phi, out, g);             \
+    const bool fast = MODE == LR_MODE_LINEAR && numerics_mode() == LR_NUMERICS_FAST;
+#define LR_LAUNCH_FWD(S, I)                                                                                          \
+    do {                                                                                                             \
+        if (fast) {                                                                                                  \
+            if (g.C == 1) warp_forward_kernel<PAD, LR_MODE_LINEAR, S, I, true, true><<<grid, blk, 0, st>>>(img, phi, out, g);   \
+            else warp_forward_kernel<PAD, LR_MODE_LINEAR, S, I, false, true><<<grid, blk, 0, st>>>(img, phi, out, g);           \
+        } else if (g.C == 1) warp_forward_kernel<PAD, MODE, S, I, true, false><<<grid, blk, 0, st>>>(img, phi, out, g);          \
+        else warp_forward_kernel<PAD, MODE, S, I, false, false><<<grid, blk, 0, st>>>(img, phi, out, g);                         \
     } while (0)
     if (scale) {
         if (ident) LR_LAUNCH_FWD(true, true);

@@ -29,24 +29,48 @@ _NET_NAMES = ["Bilinear", "identity_map", "not_normalized_identity_map", "gen_id
 _installed = False
 
 
+def _frozen_poses(self, poses):
+    """The reference builds its backprojection grid ONCE, from the poses of the first batch it ever sees, and reuses
+    it for every later batch (`self.backward_proj_grids`, model :85-87).  Same semantics here: the float32 poses of the
+    first call are cached on the module (no device-to-host copy / sync on later steps)."""
+    cached = getattr(self, "_lr_b200_poses", None)
+    if cached is None:
+        import numpy as np
+        cached = np.ascontiguousarray(poses[0].detach().cpu().numpy(), dtype=np.float32)
+        self._lr_b200_poses = cached
+    return cached
+
+
+def _dense_basis(self):
+    """The model stores `pca_vectors` as torch.from_numpy(np.load(...).T).float().cuda() (model :42): an (N,K) VIEW with
+    strides (1,N).  lr_pca_decode streams a dense row-major (N,K) basis, so the view is made contiguous ONCE and the
+    module attribute is replaced by it (same shape and values, so F.linear users are unaffected; no second 2.75 GB
+    copy stays alive, and no per-step transposition)."""
+    basis = self.pca_vectors
+    if not basis.is_contiguous():
+        basis = basis.contiguous()
+        self.pca_vectors = basis
+    return basis
+
+
 def _estimate_flow(self, moving, target_proj, poses):
     """Drop-in for reference models/LiftRegDeformSubspaceBackproj.py:80-104.
 
     Lines 85-98 (cached backprojection grid, F.grid_sample, .detach(), torch.cat with `moving`) become one kernel
-    that writes channels 1..P of the encoder input; channel 0 is a copy of `moving`.  Geometry comes from batch item
-    0 like the reference (:85-87).  Lines 99-100 (encoder, FC) are the reference's own modules; the PCA decode of :102
-    is the streaming lr_pca_decode kernel."""
+    that writes channels 1..P of the encoder input; channel 0 is a copy of `moving`.  Geometry is frozen from item 0
+    of the FIRST batch, like the reference's cached grid (:85-87).  Lines 99-100 (encoder, FC) are the reference's own
+    modules; the PCA decode of :102 is the streaming lr_pca_decode kernel."""
     import torch
     B, _, D, W, H = moving.shape
     P = target_proj.shape[1]
     x = torch.empty((B, 1 + P, D, W, H), device=moving.device, dtype=moving.dtype)
     x[:, 0:1].copy_(moving)
     with torch.no_grad():
-        _ops.backproject(target_proj.detach(), poses[0:1].detach().cpu().numpy(), (D, W, H), out=x, channel_offset=1)
+        _ops.backproject(target_proj.detach(), _frozen_poses(self, poses), (D, W, H), out=x, channel_offset=1)
     for enc in self.encoders:
         x = enc(x)
     # :102  F.linear(x, pca_vectors, pca_mean): one streaming pass over the 2.75 GB basis (lr_pca_decode)
-    disp_field = _ops.pca_decode(x, self.pca_vectors, self.pca_mean, img_shape=(D, W, H))
+    disp_field = _ops.pca_decode(x, _dense_basis(self), self.pca_mean, img_shape=(D, W, H))
     return x, disp_field
 
 

@@ -76,11 +76,17 @@ def _dp(a):
 # --------------------------------------------------------------------------- DRR
 class _DRR(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, vol, poses, rd, rh, spacing, y_norm_mode, out_scale):
+    def forward(ctx, vol, poses, rd, rh, spacing, y_norm_mode, out_scale, out):
         vol = _need_cuda_f32(vol, "vol")
         B, d, w, h = vol.shape
         n_sets, P, _ = poses.shape
-        proj = torch.empty((B, P, rd, rh), device=vol.device, dtype=torch.float32)
+        if out is None:
+            proj = torch.empty((B, P, rd, rh), device=vol.device, dtype=torch.float32)
+        else:
+            if not (out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and out.numel() == B * P * rd * rh):
+                raise ValueError("out must be a contiguous CUDA float32 tensor of %d elements" % (B * P * rd * rh))
+            proj = out
+            ctx.mark_dirty(out)
         with torch.cuda.device(vol.device):
             _native.check(_native.lib().lr_drr_forward(_ptr(vol), B, d, w, h, _dp(poses), n_sets, P, rd, rh,
                                                        _fp(spacing), y_norm_mode, out_scale, _ptr(proj), _stream()),
@@ -98,14 +104,16 @@ class _DRR(torch.autograd.Function):
             _native.check(_native.lib().lr_drr_backward(_ptr(grad_proj), B, d, w, h, _dp(poses), n_sets, P, rd, rh,
                                                         _fp(spacing), y_norm_mode, out_scale, _ptr(grad_vol), _stream()),
                           "lr_drr_backward")
-        return grad_vol, None, None, None, None, None, None
+        return grad_vol, None, None, None, None, None, None, None
 
 
-def drr_project(vol, poses, resolution, spacing, y_norm_mode=YNORM_WM1, out_scale=0.1):
+def drr_project(vol, poses, resolution, spacing, y_norm_mode=YNORM_WM1, out_scale=0.1, out=None):
     """Cone-beam DRR of vol (B,d,w,h) -> (B,P,rd,rh); differentiable wrt vol.
 
     Replaces reference sdct:59-86 (y_norm_mode=0, out_scale=0.1) and layers.py:182-187 (y_norm_mode=1, out_scale=1).
     poses: (P,3) shared by the batch, or (B,P,3); float64, voxel units.
+    out: optional pre-allocated contiguous (B,P,rd,rh) CUDA tensor (or any contiguous view with that many elements,
+    e.g. a rank's slot of an all-gather buffer) that the kernel writes into; it is returned.
     """
     poses = _poses64(poses)
     if vol.dim() != 4:
@@ -113,7 +121,7 @@ def drr_project(vol, poses, resolution, spacing, y_norm_mode=YNORM_WM1, out_scal
     if poses.shape[0] not in (1, vol.shape[0]):
         raise ValueError("poses batch (%d) must be 1 or B (%d)" % (poses.shape[0], vol.shape[0]))
     rd, rh = int(resolution[0]), int(resolution[1])
-    return _DRR.apply(vol, poses, rd, rh, _spacing3(spacing), int(y_norm_mode), float(out_scale))
+    return _DRR.apply(vol, poses, rd, rh, _spacing3(spacing), int(y_norm_mode), float(out_scale), out)
 
 
 def project_grid(poses, resolution, obj_shape, spacing, device, y_norm_mode=YNORM_WM1, flip=False, want_grid=True):
@@ -175,7 +183,12 @@ class _Backproject(torch.autograd.Function):
             _native.check(_native.lib().lr_backproject_backward(ctypes.c_void_p(gview.data_ptr()), nchan * nv, nv, _fp(poses),
                                                                 B, P, pw, ph, d, w, h, _ptr(grad_proj), _stream()),
                           "lr_backproject_backward")
-        return grad_proj, None, None, None, None, None, None, None, None
+        # `out` was overwritten in channels [off, off+P): the gradient wrt its previous content passes through elsewhere
+        grad_buf = None
+        if ctx.needs_input_grad[5]:
+            grad_buf = grad_out.clone()
+            grad_buf[:, off:off + P] = 0
+        return grad_proj, None, None, None, None, grad_buf, None, None, None
 
 
 def backproject(target_proj, poses, img_shape, out=None, channel_offset=0, slab=None):
@@ -341,6 +354,10 @@ def pca_decode(coefs, pca_vectors, pca_mean=None, img_shape=None, add_identity=F
         raise ValueError("expected coefs (B,K) and pca_vectors (N,K); got %s and %s" % (tuple(coefs.shape), tuple(pca_vectors.shape)))
     if pca_mean is not None and tuple(pca_mean.shape) != (pca_vectors.shape[0],):
         raise ValueError("pca_mean must be (N,)")
+    if not pca_vectors.is_contiguous():
+        # a silent .contiguous() here would transpose-copy the whole basis (2.75 GB at 160^3) on EVERY call
+        raise ValueError("pca_vectors must be a dense row-major (N,K) tensor; the reference builds an (N,K) view of a "
+                         "(K,N) array (model :42) -- call .contiguous() on it once (dropin.install() does)")
     D = H = W = 0
     if add_identity:
         if img_shape is None or 3 * int(np.prod(img_shape)) != pca_vectors.shape[0]:

@@ -42,16 +42,19 @@ def _world(group):
 
 # --------------------------------------------------------------------------------------------- DRR: view sharding
 def drr_project_sharded(vol, poses, resolution, spacing, y_norm_mode=0, out_scale=0.1, group=None, gather=True,
-                        project_fn=None):
+                        project_fn=None, buf=None):
     """View-sharded DRR.  vol (B,d,w,h) replicated on every rank; poses (P,3) or (B,P,3).
 
     The flattened list of (b,p) views is split contiguously across ranks; each rank projects its views and, if
     `gather`, the detector images are all-gathered so every rank returns the full (B,P,rd,rh).  With gather=False
     the rank's own (n_local,rd,rh) images are returned together with its (start, stop) range.
     `project_fn(vol_b (1,d,w,h), poses (n,3), resolution, spacing, y_norm_mode, out_scale) -> (1,n,rd,rh)` defaults
-    to the CUDA op; the CPU tests inject the oracle.
+    to the CUDA op, which writes each rank's images directly into its slot of the gather buffer (`out=`), so the
+    collective is the only copy; the CPU tests inject the oracle (whose result is copied in).
+    `buf`: optional pre-allocated (world, slot, rd, rh) gather buffer (benchmarks reuse it across calls).
     """
-    if project_fn is None:
+    native = project_fn is None
+    if native:
         from . import ops
         project_fn = ops.drr_project
     world, rank = _world(group)
@@ -65,14 +68,20 @@ def drr_project_sharded(vol, poses, resolution, spacing, y_norm_mode=0, out_scal
     ranges = all_ranges(n_views, world)
     v0, v1 = ranges[rank]
     slot = max(hi - lo for lo, hi in ranges)              # all_gather needs equal-sized contributions
-    buf = torch.zeros((world, slot, rd, rh), device=vol.device, dtype=torch.float32)
+    if buf is None:
+        buf = torch.zeros((world, slot, rd, rh), device=vol.device, dtype=torch.float32)
+    elif tuple(buf.shape) != (world, slot, rd, rh):
+        raise ValueError("buf must be (%d,%d,%d,%d)" % (world, slot, rd, rh))
     mine = buf[rank]
     v = v0
     while v < v1:                                          # one call per batch item touched by [v0, v1)
         b, p = divmod(v, P)
         p_hi = min(P, p + (v1 - v))
-        out = project_fn(vol[b:b + 1], p64[b, p:p_hi], (rd, rh), spacing, y_norm_mode, out_scale)
-        mine[v - v0:v - v0 + (p_hi - p)].copy_(out[0])
+        slot_view = mine[v - v0:v - v0 + (p_hi - p)]       # the kernel writes straight into the gather buffer
+        if native:
+            project_fn(vol[b:b + 1], p64[b, p:p_hi], (rd, rh), spacing, y_norm_mode, out_scale, out=slot_view)
+        else:
+            slot_view.copy_(project_fn(vol[b:b + 1], p64[b, p:p_hi], (rd, rh), spacing, y_norm_mode, out_scale)[0])
         v += p_hi - p
     if not gather:
         return mine[:v1 - v0], (v0, v1)
@@ -80,6 +89,8 @@ def drr_project_sharded(vol, poses, resolution, spacing, y_norm_mode=0, out_scal
         # NCCL gathers in place (the send slice already sits in the receive buffer); gloo wants a separate input
         send = mine.reshape(-1) if buf.is_cuda else mine.reshape(-1).clone()
         dist.all_gather_into_tensor(buf.view(-1), send, group=group)
+    if all(hi - lo == slot for lo, hi in ranges):         # equal shares: the gather buffer IS the result
+        return buf.view(B, P, rd, rh)
     full = torch.cat([buf[r, :hi - lo] for r, (lo, hi) in enumerate(ranges)], dim=0)
     return full.reshape(B, P, rd, rh)
 

@@ -36,6 +36,27 @@ def lib():
     return _lib
 
 
+def set_blend(mode):
+    """'aten' (default: the reference's operation order) or 'fast' (the CUDA library's LR_NUMERICS_FAST blend order:
+    same indices and weights, blends as fused lerps).  Returns the previous mode."""
+    prev = "fast" if lib().lro_get_blend() else "aten"
+    lib().lro_set_blend({"aten": 0, "fast": 1}[mode])
+    return prev
+
+
+class blend:
+    """with c_oracle.blend('fast'): ..."""
+
+    def __init__(self, mode):
+        self.mode = mode
+
+    def __enter__(self):
+        self.prev = set_blend(self.mode)
+
+    def __exit__(self, *exc):
+        set_blend(self.prev)
+
+
 def _f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 

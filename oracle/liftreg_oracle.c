@@ -53,6 +53,19 @@
 #define LRO_API __attribute__((visibility("default")))
 
 /* ------------------------------------------------------------------ */
+/* Blend order                                                        */
+/* ------------------------------------------------------------------ */
+/* 0 (default): ATen's operation order -- what the reference computes, pinned against torch and the goldens.
+ * 1: the operation order of the CUDA library's LR_NUMERICS_FAST mode (include/liftreg_b200.h): identical
+ *    coordinates, floor indices and weights; the 4-tap / 8-tap blend evaluated as fused linear interpolations
+ *    (backprojection: detector rows interpolated along axis 1, then blended along axis 0; warp: x, then y, then z,
+ *    with `using_scale` folded away and skipped taps entering as -1).  Exists so that the tests can demand BIT-EXACT
+ *    agreement from the fast kernels too (which proves their indexing), and bound fast-vs-ATen on the CPU. */
+static int g_blend = 0;
+LRO_API void lro_set_blend(int mode) { g_blend = mode != 0; }
+LRO_API int lro_get_blend(void) { return g_blend; }
+
+/* ------------------------------------------------------------------ */
 /* ATen grid_sampler semantics                                        */
 /* ------------------------------------------------------------------ */
 
@@ -97,6 +110,28 @@ static inline float sample3(const float *vol, int D, int H, int W,
     return out;
 }
 
+/* Linear sample in the fast kernels' order (g_blend == 1): taps that padding skips enter as `masked`. */
+static inline float sample3_fast(const float *vol, int D, int H, int W,
+                                 float gx, float gy, float gz, int padding, float masked) {
+    float ix = unnorm3(gx, W), iy = unnorm3(gy, H), iz = unnorm3(gz, D);
+    if (padding == 1) { ix = clipc(ix, W); iy = clipc(iy, H); iz = clipc(iz, D); }
+    float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
+    /* far outside: every tap is skipped whatever the weights are (keeps the int casts defined) */
+    if (!(fx > -4.0f && fx < (float)W + 4.0f && fy > -4.0f && fy < (float)H + 4.0f && fz > -4.0f && fz < (float)D + 4.0f))
+        return masked;
+    int64_t x0 = (int64_t)fx, y0 = (int64_t)fy, z0 = (int64_t)fz;
+    float wx1 = ix - fx, wy1 = iy - fy, wz1 = iz - fz;
+    float v[8];
+    for (int t = 0; t < 8; ++t) {
+        int64_t xx = x0 + (t & 1), yy = y0 + ((t >> 1) & 1), zz = z0 + (t >> 2);
+        v[t] = inb3(zz, yy, xx, D, H, W) ? vol[((size_t)zz * H + yy) * W + xx] : masked;
+    }
+    float c00 = fmaf(wx1, v[1] - v[0], v[0]), c10 = fmaf(wx1, v[3] - v[2], v[2]);
+    float c01 = fmaf(wx1, v[5] - v[4], v[4]), c11 = fmaf(wx1, v[7] - v[6], v[6]);
+    float d0 = fmaf(wy1, c10 - c00, c00), d1 = fmaf(wy1, c11 - c01, c01);
+    return fmaf(wz1, d1 - d0, d0);
+}
+
 /* One bilinear sample of img[H][W] at normalised (gx->W, gy->H), zeros padding. */
 static inline float sample2(const float *img, int H, int W, float gx, float gy) {
     float ix = unnorm2(gx, W), iy = unnorm2(gy, H);
@@ -111,6 +146,10 @@ static inline float sample2(const float *img, int H, int W, float gx, float gy) 
     float b = (y0 >= 0 && y0 < H && x1 >= 0 && x1 < W) ? img[(size_t)y0 * W + x1] : 0.0f;
     float c = (y1 >= 0 && y1 < H && x0 >= 0 && x0 < W) ? img[(size_t)y1 * W + x0] : 0.0f;
     float d = (y1 >= 0 && y1 < H && x1 >= 0 && x1 < W) ? img[(size_t)y1 * W + x1] : 0.0f;
+    if (g_blend) {   /* fast kernels: rows interpolated along x first, then blended along y */
+        float t_lo = fmaf(b, w, a * e), t_up = fmaf(d, w, c * e);
+        return fmaf(t_up, n, t_lo * s);
+    }
     return fmaf(d, se, fmaf(c, sw, fmaf(b, ne, a * nw)));
 }
 
@@ -350,12 +389,13 @@ LRO_API void lro_warp_forward(const float *img, const float *phi, int B, int C, 
                               int padding, int mode, int using_scale, float *out) {
     size_t nv = (size_t)D * H * W;
     float *pre = NULL;
-    if (using_scale) {
+    const int fast = g_blend && mode == 0;
+    if (using_scale && !fast) {
         pre = (float *)malloc((size_t)B * C * nv * sizeof(float));
 #pragma omp parallel for schedule(static)
         for (int64_t i = 0; i < (int64_t)((size_t)B * C * nv); ++i) pre[i] = (img[i] + 1.0f) / 2.0f;   /* :50 */
     }
-    const float *src = using_scale ? pre : img;
+    const float *src = pre ? pre : img;
 #pragma omp parallel for collapse(2) schedule(static)
     for (int b = 0; b < B; ++b)
         for (int z = 0; z < D; ++z)
@@ -365,6 +405,12 @@ LRO_API void lro_warp_forward(const float *img, const float *phi, int B, int C, 
                     const float *ph = phi + (size_t)b * 3 * nv;
                     /* forward_stn :27-30 reverses channels: grid x<-phi[2], y<-phi[1], z<-phi[0] */
                     float gx = ph[2 * nv + vox], gy = ph[nv + vox], gz = ph[vox];
+                    if (fast) {   /* :50 and :52 cancel because the weights sum to 1; a skipped tap is intensity 0 = -1 */
+                        for (int c = 0; c < C; ++c)
+                            out[((size_t)b * C + c) * nv + vox] = sample3_fast(img + ((size_t)b * C + c) * nv, D, H, W, gx, gy, gz,
+                                                                               padding, using_scale ? -1.0f : 0.0f);
+                        continue;
+                    }
                     for (int c = 0; c < C; ++c) {
                         float s = sample3(src + ((size_t)b * C + c) * nv, D, H, W, gx, gy, gz, padding, mode);
                         out[((size_t)b * C + c) * nv + vox] = using_scale ? s * 2.0f - 1.0f : s;   /* :52 */
