@@ -149,6 +149,15 @@ LR_API size_t lr_backproject_forward_host_workspace_bytes(int B, int P, int pw, 
 LR_API int lr_backproject_forward_host(const float *proj_host, const float *poses, int B, int P, int pw, int ph,
                                        int d, int w, int h, float *out_host,
                                        void *workspace, size_t workspace_bytes, lr_stream_t stream);
+/* Overlapped form of the host-buffer calls: the *_host_async entry points enqueue H2D, kernels and D2H on `stream` and
+ * return WITHOUT synchronising, so one host thread can put the backprojection on one stream and the warp on another and
+ * the two transfers share the full-duplex PCIe link (the reference's calls, sdct:70-72,97-99, are serial and blocking).
+ * Host buffers must be pinned for the copies to be asynchronous and must stay alive until the stream is synchronised:
+ * lr_stream_synchronize(stream) (for callers without a CUDA runtime binding) or cudaStreamSynchronize. */
+LR_API int lr_backproject_forward_host_async(const float *proj_host, const float *poses, int B, int P, int pw, int ph,
+                                             int d, int w, int h, float *out_host,
+                                             void *workspace, size_t workspace_bytes, lr_stream_t stream);
+LR_API int lr_stream_synchronize(lr_stream_t stream);
 
 /* ---- displacement-field warp ------------------------------------------- */
 /* replaces net_utils.py:26-56 Bilinear.forward / forward_stn.
@@ -188,6 +197,9 @@ LR_API size_t lr_warp_forward_host_workspace_bytes(int B, int C, int D, int H, i
 LR_API int lr_warp_forward_host(const float *img_host, const float *phi_host, int B, int C, int D, int H, int W,
                                 int padding, int mode, int using_scale, int disp_plus_identity, float *out_host,
                                 void *workspace, size_t workspace_bytes, lr_stream_t stream);
+LR_API int lr_warp_forward_host_async(const float *img_host, const float *phi_host, int B, int C, int D, int H, int W,
+                                      int padding, int mode, int using_scale, int disp_plus_identity, float *out_host,
+                                      void *workspace, size_t workspace_bytes, lr_stream_t stream);
 
 /* ---- PCA-subspace displacement decode ------------- */
 /* replaces models/LiftRegDeformSubspaceBackproj.py:102
@@ -217,6 +229,15 @@ LR_API int lr_warp_forward_plan(int B, int D, int H, int W, int z_count, int pla
 /* how lr_backproject_forward tiles planes, columns and rows: plan = {ichunk, isub, by, bx, n_chunks, run0, n0, run1, n1,
  * run2, n2, grid} */
 LR_API int lr_backproject_forward_plan(int B, int P, int pw, int ph, int d, int w, int h, int plan[12]);
+
+/* ---- measurement probes (diagnostics; bench.py's DRR fractions) -------------- */
+/* lr_probe_l1_gather: every block re-reads its own floats_per_block-float (power of two >= 2048) slice of buf `iters`
+ * times with coalesced 32-bit loads that hit L1: bytes moved = blocks*256*iters*32.  Timed by the caller, it gives the
+ * aggregate L1 gather bandwidth that SURVEY.md 8d names as the DRR kernel's binding resource.
+ * lr_probe_issue: blocks*256 threads each issue iters*8 independent FFMAs: the chip's sustained issue rate. */
+LR_API int lr_probe_l1_gather(const float *buf, int64_t buf_floats, int blocks, int floats_per_block, int iters,
+                              float *sink, lr_stream_t stream);
+LR_API int lr_probe_issue(int blocks, int iters, float *sink, lr_stream_t stream);
 
 /* ---- similarity loss on the warp output -------------- */
 /* replaces src/liftreg/layers/losses.py:14-29 NCCLoss.forward (training similarity, SubspaceLoss.py:27; validation score,

@@ -33,6 +33,9 @@ SIGNATURES = {
     "lr_backproj_grid": (_i, [c_float_p, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "lr_backproject_forward_host_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i]),
     "lr_backproject_forward_host": (_i, [_vp, c_float_p, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    "lr_backproject_forward_host_async": (_i, [_vp, c_float_p, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    "lr_stream_synchronize": (_i, [_vp]),
+    "lr_warp_forward_host_async": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "lr_warp_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "lr_warp_backward": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "lr_warp_forward_slab": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
@@ -45,6 +48,8 @@ SIGNATURES = {
     "lr_atten_coef": (_i, [_vp, _i64, _vp, _vp]),
     "lr_warp_forward_plan": (_i, [_i, _i, _i, _i, _i, ctypes.POINTER(ctypes.c_int)]),
     "lr_backproject_forward_plan": (_i, [_i, _i, _i, _i, _i, _i, _i, ctypes.POINTER(ctypes.c_int)]),
+    "lr_probe_l1_gather": (_i, [_vp, _i64, _i, _i, _i, _vp, _vp]),
+    "lr_probe_issue": (_i, [_i, _i, _vp, _vp]),
     "lr_ncc_sums": (_i, [_vp, _vp, _i, _i64, _vp, _vp]),
     "lr_ncc_backward": (_i, [_vp, _vp, _i, _i64, _vp, _vp, _vp, _vp]),
 }

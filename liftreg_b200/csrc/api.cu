@@ -136,9 +136,12 @@ extern "C" size_t lr_backproject_forward_host_workspace_bytes(int B, int P, int 
     return align256(sizeof(float) * (size_t)B * P * pw * ph) + align256(sizeof(float) * (size_t)B * P * d * w * h);
 }
 
-extern "C" int lr_backproject_forward_host(const float *proj_host, const float *poses, int B, int P, int pw, int ph,
-                                           int d, int w, int h, float *out_host, void *workspace,
-                                           size_t workspace_bytes, lr_stream_t stream) {
+// Asynchronous form: H2D, kernel and D2H are enqueued on `stream` and the call returns without waiting.  Two such
+// calls on two streams (e.g. this one and lr_warp_forward_host_async) overlap on the full-duplex link; the caller
+// synchronises with lr_stream_synchronize (or its own cudaStreamSynchronize) before touching out_host.
+extern "C" int lr_backproject_forward_host_async(const float *proj_host, const float *poses, int B, int P, int pw, int ph,
+                                                 int d, int w, int h, float *out_host, void *workspace,
+                                                 size_t workspace_bytes, lr_stream_t stream) {
     LR_REQUIRE(proj_host && out_host && workspace, "backproject_forward_host: null pointer");
     const size_t need = lr_backproject_forward_host_workspace_bytes(B, P, pw, ph, d, w, h);
     if (need == 0 || workspace_bytes < need) {
@@ -153,8 +156,18 @@ extern "C" int lr_backproject_forward_host(const float *proj_host, const float *
     // (Writing the 65 MB result straight to pinned host memory from the kernel was measured slower than the copy
     // engine: 1.30 vs 1.23 ms at cfg 2, so this path stays staged; the warp below does stream over PCIe itself.)
     if (int e = lr_backproject_forward(d_in, poses, B, P, pw, ph, d, w, h, d_out, (int64_t)P * d * w * h, (int64_t)d * w * h, stream)) return e;
-    if (int e = cuda_ok(cudaMemcpyAsync(out_host, d_out, out_bytes, cudaMemcpyDeviceToHost, st), "backproject_forward_host: D2H")) return e;
-    return cuda_ok(cudaStreamSynchronize(st), "backproject_forward_host: sync");
+    return cuda_ok(cudaMemcpyAsync(out_host, d_out, out_bytes, cudaMemcpyDeviceToHost, st), "backproject_forward_host: D2H");
+}
+
+extern "C" int lr_backproject_forward_host(const float *proj_host, const float *poses, int B, int P, int pw, int ph,
+                                           int d, int w, int h, float *out_host, void *workspace,
+                                           size_t workspace_bytes, lr_stream_t stream) {
+    if (int e = lr_backproject_forward_host_async(proj_host, poses, B, P, pw, ph, d, w, h, out_host, workspace, workspace_bytes, stream)) return e;
+    return cuda_ok(cudaStreamSynchronize(as_stream(stream)), "backproject_forward_host: sync");
+}
+
+extern "C" int lr_stream_synchronize(lr_stream_t stream) {
+    return cuda_ok(cudaStreamSynchronize(as_stream(stream)), "stream_synchronize");
 }
 
 // ---- warp, host buffers -----------------------------------------------------------------------------
@@ -164,9 +177,9 @@ extern "C" size_t lr_warp_forward_host_workspace_bytes(int B, int C, int D, int 
     return 2 * align256(sizeof(float) * B * C * nv) + align256(sizeof(float) * B * 3 * nv);
 }
 
-extern "C" int lr_warp_forward_host(const float *img_host, const float *phi_host, int B, int C, int D, int H, int W,
-                                    int padding, int mode, int using_scale, int disp_plus_identity, float *out_host,
-                                    void *workspace, size_t workspace_bytes, lr_stream_t stream) {
+static int warp_forward_host_enqueue(const float *img_host, const float *phi_host, int B, int C, int D, int H, int W,
+                                     int padding, int mode, int using_scale, int disp_plus_identity, float *out_host,
+                                     void *workspace, size_t workspace_bytes, lr_stream_t stream, bool allow_zero_copy) {
     LR_REQUIRE(img_host && phi_host && out_host && workspace, "warp_forward_host: null pointer");
     const size_t need = lr_warp_forward_host_workspace_bytes(B, C, D, H, W);
     if (need == 0 || workspace_bytes < need) {
@@ -181,14 +194,29 @@ extern "C" int lr_warp_forward_host(const float *img_host, const float *phi_host
     float *d_out = (float *)((char *)d_phi + align256(phi_bytes));
     if (int e = cuda_ok(cudaMemcpyAsync(d_img, img_host, img_bytes, cudaMemcpyHostToDevice, st), "warp_forward_host: H2D img")) return e;
     const void *phi_alias = nullptr, *out_alias = nullptr;
-    if (zero_copy_enabled() && host_ptr_is_mapped(phi_host, &phi_alias) && host_ptr_is_mapped(out_host, &out_alias)) {
+    if (allow_zero_copy && zero_copy_enabled() && host_ptr_is_mapped(phi_host, &phi_alias) && host_ptr_is_mapped(out_host, &out_alias)) {
         // the image is gathered 8x per voxel and must sit in HBM; the map is read once and the result written once, so
         // the kernel streams both over PCIe itself (H2D of phi, compute and D2H of the result overlap in one pass)
-        if (int e = lr_warp_forward(d_img, (const float *)phi_alias, B, C, D, H, W, padding, mode, using_scale, disp_plus_identity, (float *)out_alias, stream)) return e;
-        return cuda_ok(cudaStreamSynchronize(st), "warp_forward_host: sync");
+        return lr_warp_forward(d_img, (const float *)phi_alias, B, C, D, H, W, padding, mode, using_scale, disp_plus_identity, (float *)out_alias, stream);
     }
     if (int e = cuda_ok(cudaMemcpyAsync(d_phi, phi_host, phi_bytes, cudaMemcpyHostToDevice, st), "warp_forward_host: H2D phi")) return e;
     if (int e = lr_warp_forward(d_img, d_phi, B, C, D, H, W, padding, mode, using_scale, disp_plus_identity, d_out, stream)) return e;
-    if (int e = cuda_ok(cudaMemcpyAsync(out_host, d_out, img_bytes, cudaMemcpyDeviceToHost, st), "warp_forward_host: D2H")) return e;
-    return cuda_ok(cudaStreamSynchronize(st), "warp_forward_host: sync");
+    return cuda_ok(cudaMemcpyAsync(out_host, d_out, img_bytes, cudaMemcpyDeviceToHost, st), "warp_forward_host: D2H");
+}
+
+// The asynchronous form always stages through the copy engines: it exists to overlap with OTHER transfers (the
+// backprojection's D2H on a second stream), and there the kernel-driven PCIe streaming of the blocking form competes
+// with the copy engine for the link (measured at cfg 2, both calls in flight: 1.92 ms with it, 1.71 ms staged).
+extern "C" int lr_warp_forward_host_async(const float *img_host, const float *phi_host, int B, int C, int D, int H, int W,
+                                          int padding, int mode, int using_scale, int disp_plus_identity,
+                                          float *out_host, void *workspace, size_t workspace_bytes, lr_stream_t stream) {
+    return warp_forward_host_enqueue(img_host, phi_host, B, C, D, H, W, padding, mode, using_scale, disp_plus_identity, out_host,
+                                     workspace, workspace_bytes, stream, false);
+}
+
+extern "C" int lr_warp_forward_host(const float *img_host, const float *phi_host, int B, int C, int D, int H, int W,
+                                    int padding, int mode, int using_scale, int disp_plus_identity, float *out_host,
+                                    void *workspace, size_t workspace_bytes, lr_stream_t stream) {
+    if (int e = warp_forward_host_enqueue(img_host, phi_host, B, C, D, H, W, padding, mode, using_scale, disp_plus_identity, out_host, workspace, workspace_bytes, stream, true)) return e;
+    return cuda_ok(cudaStreamSynchronize(as_stream(stream)), "warp_forward_host: sync");
 }

@@ -311,8 +311,12 @@ __device__ __forceinline__ f32x2 bp_fetch_row(const float *lo0, const float *lo1
         const float a1 = (rv && c10) ? __ldg(q1) : 0.0f, b1 = (rv && c11) ? __ldg(q1 + 1) : 0.0f;
         va = pack2(a0, a1); vb = pack2(b0, b1);
     } else {
+#ifdef LR_BP_ABLATE_LOADS       // experiment: no gathers
+        va = pack2(__int_as_float(roff), 1.0f); vb = pack2(2.0f, __int_as_float(roff));
+#else
         const float *q0 = lo0 + (unsigned)roff, *q1 = lo1 + (unsigned)roff;
         va = pack2(__ldg(q0), __ldg(q1)); vb = pack2(__ldg(q0 + 1), __ldg(q1 + 1));
+#endif
     }
     return fma2(vb, w2, mul2(va, e2));
 }
@@ -335,8 +339,12 @@ __device__ __forceinline__ void bp_march_rows(const BpEvent *__restrict__ ev, in
                 o0[ofs] = r0v;
                 if (!CHK || has1) o1[ofs] = r1v;
             } else {
+#ifdef LR_BP_ABLATE_STORES      // experiment: (almost) no stores
+                if (r0v == 123.456f) st_stream(o0 + ofs, r1v);
+#else
                 st_stream(o0 + ofs, r0v);
                 if (!CHK || has1) st_stream(o1 + ofs, r1v);
+#endif
             }
             ofs += step;
         }
@@ -377,8 +385,13 @@ __global__ void __launch_bounds__(256)
     const f32x2 zero2 = splat2(g.zero);
 
     for (int j = j_begin; j < j_end; ++j) {
+#ifdef LR_BP_ABLATE_TABLES      // experiment: tables of the block's first row reused for all its rows, no per-row barrier
+        const int buf = 0;
+        if (tid < 32 && j == j_begin) {
+#else
         const int buf = (j - j_begin) & 1;
         if (tid < 32) {
+#endif
             // warp 0: one plane of the chunk per lane; neighbours' floor rows come by shuffle
             const float scale = view_scale(sy, g.w, j);
             const bool act = tid < i_count;
@@ -418,6 +431,9 @@ __global__ void __launch_bounds__(256)
             // the previous row's bulk copies must have read the staging tile before anyone overwrites it
             if (tid < i_count) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
+#ifdef LR_BP_ABLATE_TABLES
+        if (j == j_begin)
+#endif
         __syncthreads();
         const int fl = flags_all[buf];
         const float scale = scale_all[buf];

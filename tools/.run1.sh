@@ -1,13 +1,19 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
-LIFTREG_B200_BP_TMA=1 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "backproject or cfg3 or slab or host_entry or drop_in or 320" > gpurun_out/r2b_pytest_tma.txt 2>&1; echo "pytest rc=$?" >> gpurun_out/r2b_pytest_tma.txt
-{
-echo "== fast";  python tools/kbench.py backproject
-echo "== fast + TMA out"; LIFTREG_B200_BP_TMA=1 python tools/kbench.py backproject
-echo "== fast + TMA batch 8"; LIFTREG_B200_BP_TMA=1 python tools/kbench.py backproject --batch 8 --iters 400
-} > gpurun_out/r2b_kbench.txt 2>&1
-ncu --set full --clock-control none --import-source on -k regex:backproject_forward_rows -s 3 -c 1 -o gpurun_out/prof_r2b_bp python tools/kbench.py backproject --iters 16 > gpurun_out/ncu_r2b_bp.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:warp_forward -s 3 -c 1 -o gpurun_out/prof_r2b_warp python tools/kbench.py warp --iters 16 > gpurun_out/ncu_r2b_warp.log 2>&1
-LIFTREG_B200_BP_TMA=1 ncu --set full --clock-control none --import-source on -k regex:backproject_forward_rows -s 3 -c 1 -o gpurun_out/prof_r2b_bp_tma python tools/kbench.py backproject --iters 16 > gpurun_out/ncu_r2b_bp_tma.log 2>&1
-tail -3 gpurun_out/r2b_pytest_tma.txt; cat gpurun_out/r2b_kbench.txt
+nvidia-smi -L
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/r2e_bench_n2.json 2> gpurun_out/r2e_bench_n2.err
+echo "rc=$?"; tail -5 gpurun_out/r2e_bench_n2.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --impl reference --steps 3 --warmup 1 > gpurun_out/r2e_bench_n2_ref.json 2> gpurun_out/r2e_bench_n2_ref.err
+echo "ref rc=$?"; cat gpurun_out/r2e_bench_n2_ref.json | cut -c1-400
+LIFTREG_B200_ZERO_COPY=0 python bench.py --steps 20 --warmup 3 --no-extras --no-cpu-baseline > gpurun_out/r2e_bench_staged.json 2> gpurun_out/r2e_bench_staged.err
+python bench.py --steps 20 --warmup 3 --no-extras --no-cpu-baseline > gpurun_out/r2e_bench_zc.json 2> gpurun_out/r2e_bench_zc.err
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/r2e_bench_n2.json'))
+for k in ('value','ms_per_step','n_gpus','e2e','cfg4_drr_view_sharded','cfg5_training_ops','sharded_parity','config'):
+    print(k, json.dumps(d.get(k))[:1000])
+for f in ('staged','zc'):
+    d=json.load(open('gpurun_out/r2e_bench_%s.json'%f)); print(f, d['e2e']['ms_per_step'], d['e2e']['serial']['ms_per_step'], d['value'])
+PY
+timeout 600 python -m pytest tests/test_multigpu_nccl.py -m gpu -x -q 2>&1 | tail -3
