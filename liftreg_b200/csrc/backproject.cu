@@ -51,7 +51,6 @@ struct BpDims {
     int64_t proj_view_stride;      // pw*ph
     int64_t out_batch_stride, out_chan_stride;
     float zero;                    // +0.0f the compiler cannot constant-fold (see mul2_sep)
-    int tma_out;                   // rows kernel: output rows leave through shared memory + cp.async.bulk (TMA)
 };
 
 struct AxisTap {      // one axis of the bilinear footprint
@@ -139,7 +138,7 @@ __device__ __forceinline__ float bilerp_sep(float va, float vb, float vc, float 
 }
 
 // Zeros-padding path of one voxel column (k): per-tap predicates, scalar arithmetic.
-template <bool SEP, bool TO_SMEM = false>
+template <bool SEP>
 __device__ __forceinline__ void backproject_column_checked(const float *pvf, char *o, int64_t plane_bytes, const BpRow *rows,
                                                            int ii0, int ii1, int ph, bool c0, bool c1, float e, float wq) {
     for (int ii = ii0; ii < ii1; ++ii) {
@@ -150,8 +149,7 @@ __device__ __forceinline__ void backproject_column_checked(const float *pvf, cha
         const float va = (rv0 && c0) ? __ldg(q0) : 0.0f, vb = (rv0 && c1) ? __ldg(q0 + 1) : 0.0f;
         const float vc = (rv1 && c0) ? __ldg(q1) : 0.0f, vd = (rv1 && c1) ? __ldg(q1 + 1) : 0.0f;
         const float res = SEP ? bilerp_sep(va, vb, vc, vd, r.s, r.n, e, wq) : bilerp(va, vb, vc, vd, r.s, r.n, e, wq);
-        if (TO_SMEM) *(float *)o = res;       // staging tile of the TMA variant (st.global cannot address shared memory)
-        else st_stream((float *)o, res);
+        st_stream((float *)o, res);
         o += plane_bytes;
     }
 }
@@ -277,27 +275,26 @@ __global__ void __launch_bounds__(256)
 // instead of planes: consecutive planes move 1..1.4 rows down the detector (the magnification), so every row of the
 // chunk's range is fetched exactly once, its T computed once (2 packed ops for the thread's two columns) and blended
 // into the plane that ends at that row, if any (2 packed ops).  Per plane that is ~25 issue slots instead of ~38 for the
-// plane-driven window of the exact kernel (whose predicated-off row fetches still issue), and the per-row set-up is
-// half: warp 0 builds the chunk's tables with shuffles, everyone else only derives its two column taps (packed).
+// plane-driven window of the exact kernel (whose predicated-off row fetches still issue).
 //
-// Tables (double-buffered over the rows j a block walks):
+// Tables, built ONCE per block for all the rows j of its run (one warp per row, in parallel, neighbours' floor rows by
+// shuffle), then a single barrier; the rows are marched without any further synchronisation:
 //   ev[slot]  slot = detector row - r_base.  n >= 0: the plane whose upper row this is, with row weight n; n < 0: none.
 //             roff = row * ph, or -1 when the row is outside the detector (its T is exactly +0: zeros padding).
 //   sub_lo/hi first (fetch only) and last slot of each sub-chunk of planes (one threadIdx.y slice).
 //   rows      the per-plane table of the generic path: taken by a (block, j) whose planes do not move strictly down the
 //             detector (magnification < 1, clamped far-outside coordinates) or span more than BP_EV_MAX rows.
-// With g.tma_out the block's output rows (h floats each, contiguous in HBM) are staged in shared memory and leave
-// through cp.async.bulk (TMA) instead of 128 B LSU stores: stores cost 2.8 L1 wavefronts per 128 B, a third of all.
+// (Measured and dropped, profiles/README.md round 2: staging the block's output rows in shared memory and writing them
+// with cp.async.bulk -- 39 us vs 23 us; a precomputed geometry plan read from global memory -- see further down.)
 constexpr int BP_EV_MAX = 112;
 constexpr int BP_MAX_SUB = 8;
-static_assert(BP_ICHUNK <= 32, "warp 0 builds the chunk tables with one plane per lane");
+constexpr int BP_JS_MAX = 4;       // rows j per block (the longest run)
+static_assert(BP_ICHUNK <= 32, "one warp builds a row's tables with one plane per lane");
 
 struct __align__(8) BpEvent {
     float n;
     int roff;
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 template <bool CHK>
 __device__ __forceinline__ f32x2 bp_fetch_row(const float *lo0, const float *lo1, int roff, f32x2 e2, f32x2 w2, bool c00,
@@ -311,23 +308,31 @@ __device__ __forceinline__ f32x2 bp_fetch_row(const float *lo0, const float *lo1
         const float a1 = (rv && c10) ? __ldg(q1) : 0.0f, b1 = (rv && c11) ? __ldg(q1 + 1) : 0.0f;
         va = pack2(a0, a1); vb = pack2(b0, b1);
     } else {
-#ifdef LR_BP_ABLATE_LOADS       // experiment: no gathers
-        va = pack2(__int_as_float(roff), 1.0f); vb = pack2(2.0f, __int_as_float(roff));
-#else
         const float *q0 = lo0 + (unsigned)roff, *q1 = lo1 + (unsigned)roff;
         va = pack2(__ldg(q0), __ldg(q1)); vb = pack2(__ldg(q0 + 1), __ldg(q1 + 1));
-#endif
     }
     return fma2(vb, w2, mul2(va, e2));
 }
 
-// One thread's two columns over one sub-chunk of planes.  TMA: results go to the block's staging tile (row pitch h floats)
-template <bool CHK, bool TMA>
+#ifndef LR_BP_UNROLL
+#define LR_BP_UNROLL 4
+#endif
+#define LR_STR2(x) #x
+#define LR_STR(x) LR_STR2(x)
+#define LR_BP_UNROLL_PRAGMA _Pragma(LR_STR(unroll LR_BP_UNROLL))
+#ifdef LR_BP_ROWS_MINB          // kernel experiments: explicit register cap
+#define LR_BP_ROWS_BOUNDS __launch_bounds__(LR_BP_ROWS_MAXT, LR_BP_ROWS_MINB)
+#else
+#define LR_BP_ROWS_BOUNDS __launch_bounds__(256)      // ptxas settles on 64 registers (6 blocks of 160 threads per SM)
+#endif
+
+// One thread's two columns over one sub-chunk of planes.
+template <bool CHK>
 __device__ __forceinline__ void bp_march_rows(const BpEvent *__restrict__ ev, int s_lo, int s_hi, const float *lo0,
                                               const float *lo1, float *o0, float *o1, unsigned ofs, unsigned step,
                                               f32x2 e2, f32x2 w2, bool c00, bool c01, bool c10, bool c11, bool has1) {
     f32x2 t_prev = bp_fetch_row<CHK>(lo0, lo1, ev[s_lo].roff, e2, w2, c00, c01, c10, c11);
-#pragma unroll 4
+    LR_BP_UNROLL_PRAGMA
     for (int s = s_lo + 1; s <= s_hi; ++s) {
         const BpEvent e = ev[s];
         const f32x2 t = bp_fetch_row<CHK>(lo0, lo1, e.roff, e2, w2, c00, c01, c10, c11);
@@ -335,32 +340,21 @@ __device__ __forceinline__ void bp_march_rows(const BpEvent *__restrict__ ev, in
             const f32x2 n2 = splat2(e.n), s2 = splat2(sub_rn(1.0f, e.n));
             float r0v, r1v;
             unpack2(fma2(t, n2, mul2(t_prev, s2)), r0v, r1v);
-            if (TMA) {
-                o0[ofs] = r0v;
-                if (!CHK || has1) o1[ofs] = r1v;
-            } else {
-#ifdef LR_BP_ABLATE_STORES      // experiment: (almost) no stores
-                if (r0v == 123.456f) st_stream(o0 + ofs, r1v);
-#else
-                st_stream(o0 + ofs, r0v);
-                if (!CHK || has1) st_stream(o1 + ofs, r1v);
-#endif
-            }
+            st_stream(o0 + ofs, r0v);
+            if (!CHK || has1) st_stream(o1 + ofs, r1v);
             ofs += step;
         }
         t_prev = t;
     }
 }
 
-template <bool TMA>
-__global__ void __launch_bounds__(256)
+__global__ void LR_BP_ROWS_BOUNDS
     backproject_forward_rows_kernel(const float *__restrict__ proj, float *__restrict__ out, BpDims g, BpPoses poses) {
-    __shared__ BpEvent ev_all[2][BP_EV_MAX];
-    __shared__ BpRow rows_all[2][BP_ICHUNK];
-    __shared__ int sub_lo[2][BP_MAX_SUB], sub_hi[2][BP_MAX_SUB];
-    __shared__ float scale_all[2];
-    __shared__ int flags_all[2];
-    extern __shared__ __align__(128) float stage[];      // TMA: [ichunk][h] output tile of the current row j
+    __shared__ BpEvent ev_all[BP_JS_MAX][BP_EV_MAX];
+    __shared__ BpRow rows_all[BP_JS_MAX][BP_ICHUNK];
+    __shared__ int sub_lo[BP_JS_MAX][BP_MAX_SUB], sub_hi[BP_JS_MAX][BP_MAX_SUB];
+    __shared__ float scale_all[BP_JS_MAX];
+    __shared__ int flags_all[BP_JS_MAX];
 
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
     int L = blockIdx.x, nj = g.nj0, js = g.js0, j_base = 0;      // block index -> (run of rows, chunk, view, batch item)
@@ -384,126 +378,255 @@ __global__ void __launch_bounds__(256)
     float *ob0 = out + bi * g.out_batch_stride + (int64_t)p * g.out_chan_stride + (int64_t)i_begin * g.w * g.h;
     const f32x2 zero2 = splat2(g.zero);
 
-    for (int j = j_begin; j < j_end; ++j) {
-#ifdef LR_BP_ABLATE_TABLES      // experiment: tables of the block's first row reused for all its rows, no per-row barrier
-        const int buf = 0;
-        if (tid < 32 && j == j_begin) {
-#else
-        const int buf = (j - j_begin) & 1;
-        if (tid < 32) {
-#endif
-            // warp 0: one plane of the chunk per lane; neighbours' floor rows come by shuffle
-            const float scale = view_scale(sy, g.w, j);
-            const bool act = tid < i_count;
-            const AxisTap t = axis_tap((float)(g.i_off + i_begin + (act ? tid : 0)) - g.half_d, sx, scale, g.div_pw, g.hpw);
-            const int r0 = t.i0;
-            const int r_prev = __shfl_up_sync(0xffffffffu, r0, 1);
-            const int r_base = __shfl_sync(0xffffffffu, r0, 0);
-            const int r_last = __shfl_sync(0xffffffffu, r0, i_count - 1);
-            const bool mono = tid == 0 || !act || r0 > r_prev;
-            const bool fast = __all_sync(0xffffffffu, mono) && (r_last + 1 - r_base < BP_EV_MAX);
-            if (act) {
-                BpRow r;
-                r.off0 = r0 * g.ph; r.n = t.w1; r.s = sub_rn(1.0f, t.w1);
-                r.mask = ((unsigned)r0 < (unsigned)g.pw ? 1 : 0) | ((unsigned)(r0 + 1) < (unsigned)g.pw ? 2 : 0);
-                rows_all[buf][tid] = r;
-                if (fast) {
-                    BpEvent *ev = ev_all[buf];
-                    const int slot = r0 + 1 - r_base;
-                    for (int s = tid == 0 ? 0 : r_prev + 2 - r_base; s < slot; ++s) {      // rows no plane ends at
-                        const int r = r_base + s;
-                        BpEvent e; e.n = -1.0f; e.roff = (unsigned)r < (unsigned)g.pw ? r * g.ph : -1;
-                        ev[s] = e;
-                    }
-                    BpEvent e; e.n = t.w1; e.roff = (unsigned)(r0 + 1) < (unsigned)g.pw ? (r0 + 1) * g.ph : -1;
-                    ev[slot] = e;
-                    const int sub = tid / g.isub, rem = tid - sub * g.isub;
-                    if (rem == 0) sub_lo[buf][sub] = slot - 1;
-                    if (rem == g.isub - 1 || tid == i_count - 1) sub_hi[buf][sub] = slot;
-                }
-            }
-            if (tid == 0) {
-                scale_all[buf] = scale;
-                flags_all[buf] = (fast ? 1 : 0) | ((r_base >= 0 && r_last + 1 < g.pw) ? 2 : 0);
-            }
-        }
-        if (TMA) {
-            // the previous row's bulk copies must have read the staging tile before anyone overwrites it
-            if (tid < i_count) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        }
-#ifdef LR_BP_ABLATE_TABLES
-        if (j == j_begin)
-#endif
-        __syncthreads();
-        const int fl = flags_all[buf];
-        const float scale = scale_all[buf];
-        const BpRow *rows = rows_all[buf];
-
-        if (ii0 < ii1) {
-            for (int q = threadIdx.x; q < g.hp; q += blockDim.x) {
-                const int k0 = q, k1 = q + g.hp;
-                const bool has1 = k1 < g.h;
-                // both column taps as one packed chain (same op sequence as axis_tap)
-                const f32x2 cen = pack2((float)k0 - g.half_h, (float)(has1 ? k1 : k0) - g.half_h), sz2 = splat2(sz);
-                const f32x2 a = add2(mul2_sep(sub2(cen, sz2), splat2(scale), zero2), sz2);
-                const f32x2 gq = mul2(div_const2(a, g.div_ph), splat2(2.0f));
-                f32x2 ix = mul2(add2(gq, splat2(1.0f)), splat2(g.hph));
-                float ixa, ixb;
-                unpack2(ix, ixa, ixb);
-                const float hi = g.hph * 2.0f + 3.0f;
-                ix = pack2(clamp_index(ixa, hi), clamp_index(ixb, hi));
-                f32x2 fl2;
-                int c0, c1;
-                floor2_fi(ix, fl2, c0, c1);
-                const f32x2 w2 = sub2(ix, fl2), e2 = sub2(splat2(1.0f), w2);
-                const bool c00 = (unsigned)c0 < (unsigned)g.ph, c01 = (unsigned)(c0 + 1) < (unsigned)g.ph;
-                const bool c10 = has1 && (unsigned)c1 < (unsigned)g.ph, c11 = has1 && (unsigned)(c1 + 1) < (unsigned)g.ph;
-                float *ob = ob0 + (unsigned)(j * g.h);
-                if (fl & 1) {
-                    const int s_lo = sub_lo[buf][threadIdx.y], s_hi = sub_hi[buf][threadIdx.y];
-                    const float *lo0 = opaque(pv0 + c0), *lo1 = opaque(pv0 + c1);
-                    const bool interior = has1 && c00 && c01 && c10 && c11;
-                    const bool hot = (fl & 2) && __all_sync(__activemask(), interior);
-                    if (TMA) {
-                        float *o0 = stage + k0, *o1 = stage + k1;
-                        const unsigned ofs = (unsigned)(ii0 * g.h);
-                        if (hot) bp_march_rows<false, true>(ev_all[buf], s_lo, s_hi, lo0, lo1, o0, o1, ofs, (unsigned)g.h, e2, w2, c00, c01, c10, c11, has1);
-                        else bp_march_rows<true, true>(ev_all[buf], s_lo, s_hi, lo0, lo1, o0, o1, ofs, (unsigned)g.h, e2, w2, c00, c01, c10, c11, has1);
-                    } else {
-                        float *o0 = opaque(ob + k0), *o1 = opaque(ob + k1);
-                        const unsigned ofs = (unsigned)ii0 * plane;
-                        if (hot) bp_march_rows<false, false>(ev_all[buf], s_lo, s_hi, lo0, lo1, o0, o1, ofs, plane, e2, w2, c00, c01, c10, c11, has1);
-                        else bp_march_rows<true, false>(ev_all[buf], s_lo, s_hi, lo0, lo1, o0, o1, ofs, plane, e2, w2, c00, c01, c10, c11, has1);
-                    }
-                } else {
-                    // generic geometry: per-plane table, per-tap predicates, same separable blend
-                    float wq0, wq1, e0, e1;
-                    unpack2(w2, wq0, wq1); unpack2(e2, e0, e1);
-                    if (TMA) {
-                        backproject_column_checked<true, true>(pv0 + c0, (char *)(stage + k0) + ii0 * g.h * 4, (int64_t)g.h * 4, rows, ii0, ii1, g.ph, c00, c01, e0, wq0);
-                        if (has1) backproject_column_checked<true, true>(pv0 + c1, (char *)(stage + k1) + ii0 * g.h * 4, (int64_t)g.h * 4, rows, ii0, ii1, g.ph, c10, c11, e1, wq1);
-                    } else {
-                        backproject_column_checked<true>(pv0 + c0, (char *)(ob + k0) + ii0 * plane_bytes, plane_bytes, rows, ii0, ii1, g.ph, c00, c01, e0, wq0);
-                        if (has1) backproject_column_checked<true>(pv0 + c1, (char *)(ob + k1) + ii0 * plane_bytes, plane_bytes, rows, ii0, ii1, g.ph, c10, c11, e1, wq1);
+    // ---- phase A: the tables of every row of the run, one (complete) warp per row, lane = plane of the chunk
+    {
+        const int warp = tid >> 5, lane = tid & 31, n_full = (int)(blockDim.x * blockDim.y) >> 5;
+        if (warp < n_full) {
+            for (int jr = warp; jr < j_end - j_begin; jr += n_full) {
+                const int j = j_begin + jr;
+                const float scale = view_scale(sy, g.w, j);
+                const bool act = lane < i_count;
+                const AxisTap t = axis_tap((float)(g.i_off + i_begin + (act ? lane : 0)) - g.half_d, sx, scale, g.div_pw, g.hpw);
+                const int r0 = t.i0;
+                const int r_prev = __shfl_up_sync(0xffffffffu, r0, 1);
+                const int r_base = __shfl_sync(0xffffffffu, r0, 0);
+                const int r_last = __shfl_sync(0xffffffffu, r0, i_count - 1);
+                const bool mono = lane == 0 || !act || r0 > r_prev;
+                const bool fast = __all_sync(0xffffffffu, mono) && (r_last + 1 - r_base < BP_EV_MAX);
+                if (act) {
+                    BpRow r;
+                    r.off0 = r0 * g.ph; r.n = t.w1; r.s = sub_rn(1.0f, t.w1);
+                    r.mask = ((unsigned)r0 < (unsigned)g.pw ? 1 : 0) | ((unsigned)(r0 + 1) < (unsigned)g.pw ? 2 : 0);
+                    rows_all[jr][lane] = r;
+                    if (fast) {
+                        BpEvent *ev = ev_all[jr];
+                        const int slot = r0 + 1 - r_base;
+                        for (int s = lane == 0 ? 0 : r_prev + 2 - r_base; s < slot; ++s) {      // rows no plane ends at
+                            const int r = r_base + s;
+                            BpEvent e; e.n = -1.0f; e.roff = (unsigned)r < (unsigned)g.pw ? r * g.ph : -1;
+                            ev[s] = e;
+                        }
+                        BpEvent e; e.n = t.w1; e.roff = (unsigned)(r0 + 1) < (unsigned)g.pw ? (r0 + 1) * g.ph : -1;
+                        ev[slot] = e;
+                        const int sub = lane / g.isub, rem = lane - sub * g.isub;
+                        if (rem == 0) sub_lo[jr][sub] = slot - 1;
+                        if (rem == g.isub - 1 || lane == i_count - 1) sub_hi[jr][sub] = slot;
                     }
                 }
-            }
-        }
-        if (TMA) {
-            // staging tile complete -> one bulk copy per plane row (h*4 bytes, 16 B aligned: checked on the host)
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncthreads();
-            if (tid < i_count) {
-                float *dst = ob0 + (unsigned)(j * g.h) + (unsigned)tid * plane;
-                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
-                             "r"(smem_u32(stage + tid * g.h)), "r"(g.h * 4)
-                             : "memory");
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                if (lane == 0) {
+                    scale_all[jr] = scale;
+                    flags_all[jr] = (fast ? 1 : 0) | ((r_base >= 0 && r_last + 1 < g.pw) ? 2 : 0);
+                }
             }
         }
     }
-    if (TMA) {
-        if (tid < i_count) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    __syncthreads();
+    if (ii0 >= ii1) return;
+
+    // ---- phase B: march the rows, no further synchronisation
+    for (int j = j_begin; j < j_end; ++j) {
+        const int jr = j - j_begin;
+        const int fl = flags_all[jr];
+        const float scale = scale_all[jr];
+        const BpRow *rows = rows_all[jr];
+        for (int q = threadIdx.x; q < g.hp; q += blockDim.x) {
+            const int k0 = q, k1 = q + g.hp;
+            const bool has1 = k1 < g.h;
+            // both column taps as one packed chain (same op sequence as axis_tap)
+            const f32x2 cen = pack2((float)k0 - g.half_h, (float)(has1 ? k1 : k0) - g.half_h), sz2 = splat2(sz);
+            const f32x2 a = add2(mul2_sep(sub2(cen, sz2), splat2(scale), zero2), sz2);
+            const f32x2 gq = mul2(div_const2(a, g.div_ph), splat2(2.0f));
+            f32x2 ix = mul2(add2(gq, splat2(1.0f)), splat2(g.hph));
+            float ixa, ixb;
+            unpack2(ix, ixa, ixb);
+            const float hi = g.hph * 2.0f + 3.0f;
+            ix = pack2(clamp_index(ixa, hi), clamp_index(ixb, hi));
+            f32x2 fl2;
+            int c0, c1;
+            floor2_fi(ix, fl2, c0, c1);
+            const f32x2 w2 = sub2(ix, fl2), e2 = sub2(splat2(1.0f), w2);
+            const bool c00 = (unsigned)c0 < (unsigned)g.ph, c01 = (unsigned)(c0 + 1) < (unsigned)g.ph;
+            const bool c10 = has1 && (unsigned)c1 < (unsigned)g.ph, c11 = has1 && (unsigned)(c1 + 1) < (unsigned)g.ph;
+            float *ob = ob0 + (unsigned)(j * g.h);
+            if (fl & 1) {
+                const int s_lo = sub_lo[jr][threadIdx.y], s_hi = sub_hi[jr][threadIdx.y];
+                const float *lo0 = opaque(pv0 + c0), *lo1 = opaque(pv0 + c1);
+                const bool interior = has1 && c00 && c01 && c10 && c11;
+                const bool hot = (fl & 2) && __all_sync(__activemask(), interior);
+                float *o0 = opaque(ob + k0), *o1 = opaque(ob + k1);
+                const unsigned ofs = (unsigned)ii0 * plane;
+                if (hot) bp_march_rows<false>(ev_all[jr], s_lo, s_hi, lo0, lo1, o0, o1, ofs, plane, e2, w2, c00, c01, c10, c11, has1);
+                else bp_march_rows<true>(ev_all[jr], s_lo, s_hi, lo0, lo1, o0, o1, ofs, plane, e2, w2, c00, c01, c10, c11, has1);
+            } else {
+                // generic geometry: per-plane table, per-tap predicates, same separable blend
+                float wq0, wq1, e0, e1;
+                unpack2(w2, wq0, wq1); unpack2(e2, e0, e1);
+                backproject_column_checked<true>(pv0 + c0, (char *)(ob + k0) + ii0 * plane_bytes, plane_bytes, rows, ii0, ii1, g.ph, c00, c01, e0, wq0);
+                if (has1) backproject_column_checked<true>(pv0 + c1, (char *)(ob + k1) + ii0 * plane_bytes, plane_bytes, rows, ii0, ii1, g.ph, c10, c11, e1, wq1);
+            }
+        }
+    }
+}
+
+// ---- forward with a precomputed geometry plan ---------------------------------------------------------------------
+// The tables the rows kernel rebuilds for every (block, row j) depend on the GEOMETRY only (poses and shapes), which a
+// registration run fixes once -- the reference caches its 131 MB sample grid for the same reason
+// (LiftRegDeformSubspaceBackproj.py:85-87: `self.backward_proj_grids`).  lr_backproject_plan_build evaluates them once
+// into a caller-owned device buffer (3 MB at cfg 2, L2-resident) and backproject_forward_plan_kernel only marches:
+// no shared memory, no barrier, no division, no axis_tap chain in the hot kernel.  MEASURED (profiles/README.md, round 2):
+// 30.4 us against 23.4 us for the rows kernel at cfg 2 -- the per-row table entry becomes a dependent global load (L2
+// latency) at the head of every gather, which costs more than rebuilding the tables in shared memory.  The entry
+// points are kept (any z-slab / stride, bit-identical results, tested) but ops.backproject does not use them.
+// One record per (view p, coronal row j), 16-byte aligned, all 4-byte words:
+//   [0] r_base   floor detector row of plane 0      [1] flags  bit 0: planes move strictly down the detector and the
+//   [2] n_slots  rows r_base .. r_base+n_slots-1         row range fits the event table (fast path allowed)
+//   rowtab[d]    (int r0, float n)      per plane: floor row and upper-row weight (generic path; slot = r0 - r_base)
+//   evtab[EVP]   (float n, int roff)    per detector row: see BpEvent
+//   coltab[h]    (int c, float wq)      per voxel column: floor detector column and upper-column weight
+struct BpPlanLayout {
+    int d, h, evp;          // planes, columns, event slots per record
+    int rec_words;          // record pitch in 4-byte words (multiple of 4)
+    __host__ __device__ int rowtab() const { return 4; }
+    __host__ __device__ int evtab() const { return 4 + 2 * d; }
+    __host__ __device__ int coltab() const { return 4 + 2 * d + 2 * evp; }
+};
+static BpPlanLayout plan_layout(int d, int h) {
+    BpPlanLayout L;
+    L.d = d; L.h = h;
+    L.evp = 3 * d + 8;
+    L.rec_words = (4 + 2 * d + 2 * L.evp + 2 * h + 3) & ~3;
+    return L;
+}
+
+// grid (w, P); block 256.  Uses the same axis_tap chain as the kernels, so every index and weight is the reference's.
+__global__ void __launch_bounds__(256) backproject_plan_kernel(int *__restrict__ plan, BpPlanLayout L, BpDims g, BpPoses poses) {
+    const int j = blockIdx.x, pl = blockIdx.y, p = g.p0 + pl;
+    int *rec = plan + ((int64_t)p * g.w + j) * L.rec_words;
+    const float sx = poses.s[pl][0], sy = poses.s[pl][1], sz = poses.s[pl][2];
+    const float scale = view_scale(sy, g.w, j);
+    int2 *rowtab = reinterpret_cast<int2 *>(rec + L.rowtab());
+    int2 *evtab = reinterpret_cast<int2 *>(rec + L.evtab());
+    int2 *coltab = reinterpret_cast<int2 *>(rec + L.coltab());
+    for (int i = threadIdx.x; i < L.d; i += blockDim.x) {
+        const AxisTap t = axis_tap((float)i - g.half_d, sx, scale, g.div_pw, g.hpw);
+        rowtab[i] = make_int2(t.i0, __float_as_int(t.w1));
+    }
+    for (int k = threadIdx.x; k < L.h; k += blockDim.x) {
+        const AxisTap t = axis_tap((float)k - g.half_h, sz, scale, g.div_ph, g.hph);
+        coltab[k] = make_int2(t.i0, __float_as_int(t.w1));
+    }
+    __syncthreads();                                 // this block's global writes are visible to the block
+    const int r_base = rowtab[0].x, r_last = rowtab[L.d - 1].x;
+    int mono = 1;
+    for (int i = threadIdx.x + 1; i < L.d; i += blockDim.x) mono &= rowtab[i].x > rowtab[i - 1].x;
+    const int n_slots = r_last + 2 - r_base;
+    const bool fast = __syncthreads_and(mono) && n_slots <= L.evp && n_slots >= 2;
+    if (fast) {
+        for (int i = threadIdx.x; i < L.d; i += blockDim.x) {
+            const int2 t = rowtab[i];
+            const int slot = t.x + 1 - r_base;
+            for (int s2 = i == 0 ? 0 : rowtab[i - 1].x + 2 - r_base; s2 < slot; ++s2) {      // rows no plane ends at
+                const int r = r_base + s2;
+                evtab[s2] = make_int2(__float_as_int(-1.0f), (unsigned)r < (unsigned)g.pw ? r * g.ph : -1);
+            }
+            evtab[slot] = make_int2(t.y, (unsigned)(t.x + 1) < (unsigned)g.pw ? (t.x + 1) * g.ph : -1);
+        }
+    }
+    if (threadIdx.x == 0) { rec[0] = r_base; rec[1] = fast ? 1 : 0; rec[2] = n_slots; rec[3] = 0; }
+}
+
+// Generic geometry from the plan: per-plane (r0, n), per-tap predicates, separable blend (as the rows kernel's generic path)
+__device__ __forceinline__ void backproject_column_plan_checked(const float *pvf, float *o, unsigned plane, const int2 *__restrict__ rowtab,
+                                                                int ia, int ib, int pw, int ph, bool c0, bool c1, float e, float wq) {
+    for (int i = ia; i < ib; ++i) {
+        const int2 t = __ldg(rowtab + i);
+        const float n = __int_as_float(t.y), s = sub_rn(1.0f, n);
+        const bool rv0 = (unsigned)t.x < (unsigned)pw, rv1 = (unsigned)(t.x + 1) < (unsigned)pw;
+        const float *q0 = pvf + t.x * ph, *q1 = q0 + ph;
+        const float va = (rv0 && c0) ? __ldg(q0) : 0.0f, vb = (rv0 && c1) ? __ldg(q0 + 1) : 0.0f;
+        const float vc = (rv1 && c0) ? __ldg(q1) : 0.0f, vd = (rv1 && c1) ? __ldg(q1 + 1) : 0.0f;
+        st_stream(o, bilerp_sep(va, vb, vc, vd, s, n, e, wq));
+        o += plane;
+    }
+}
+
+template <bool CHK>
+__device__ __forceinline__ void bp_march_plan(const int2 *__restrict__ ev, int s_lo, int s_hi, const float *lo0, const float *lo1,
+                                              float *o0, float *o1, unsigned plane, f32x2 e2, f32x2 w2, bool c00, bool c01,
+                                              bool c10, bool c11, bool has1) {
+    f32x2 t_prev = bp_fetch_row<CHK>(lo0, lo1, __ldg(ev + s_lo).y, e2, w2, c00, c01, c10, c11);
+    unsigned ofs = 0;
+#pragma unroll 4
+    for (int s = s_lo + 1; s <= s_hi; ++s) {
+        const int2 e = __ldg(ev + s);
+        const f32x2 t = bp_fetch_row<CHK>(lo0, lo1, e.y, e2, w2, c00, c01, c10, c11);
+        const float n = __int_as_float(e.x);
+        if (n >= 0.0f) {
+            const f32x2 n2 = splat2(n), s2 = splat2(sub_rn(1.0f, n));
+            float r0v, r1v;
+            unpack2(fma2(t, n2, mul2(t_prev, s2)), r0v, r1v);
+            st_stream(o0 + ofs, r0v);
+            if (!CHK || has1) st_stream(o1 + ofs, r1v);
+            ofs += plane;
+        }
+        t_prev = t;
+    }
+}
+
+// Same launch shape as the rows kernel: block = (batch item, view, chunk of planes, run of rows j); threads = column
+// pairs x sub-chunks of planes.  Blocks share nothing: the grouping only sets the dispatch order (long runs first).
+__global__ void __launch_bounds__(256)
+    backproject_forward_plan_kernel(const float *__restrict__ proj, float *__restrict__ out, const int *__restrict__ plan,
+                                    BpPlanLayout L, BpDims g) {
+    int Lb = blockIdx.x, nj = g.nj0, js = g.js0, j_base = 0;
+    if (Lb >= g.nj0 * g.n_vc) {
+        Lb -= g.nj0 * g.n_vc; nj = g.nj1; js = g.js1; j_base = g.nj0 * g.js0;
+        if (Lb >= g.nj1 * g.n_vc) { Lb -= g.nj1 * g.n_vc; nj = g.nj2; js = g.js2; j_base += g.nj1 * g.js1; }
+    }
+    const int vc = Lb / nj;
+    const int bv = vc / g.n_chunks;
+    const int bi = bv / g.n_views;
+    const int p = g.p0 + (bv - bi * g.n_views);
+    const int i_begin = (vc - bv * g.n_chunks) * g.ichunk;
+    const int i_count = min(g.ichunk, g.d - i_begin);
+    const int j_begin = j_base + (Lb - vc * nj) * js, j_end = min(g.w, j_begin + js);
+    const int ii0 = threadIdx.y * g.isub, ii1 = min(i_count, ii0 + g.isub);
+    if (ii0 >= ii1) return;
+    const int ia = g.i_off + i_begin + ii0, ib = g.i_off + i_begin + ii1;     // absolute planes [ia, ib) of this thread
+    const unsigned plane = (unsigned)(g.w * g.h);
+    const float *pv0 = proj + bi * ((int64_t)g.P * g.proj_view_stride) + (int64_t)p * g.proj_view_stride;
+    float *ob0 = out + bi * g.out_batch_stride + (int64_t)p * g.out_chan_stride + (int64_t)(i_begin + ii0) * g.w * g.h;
+    const int *rec = plan + ((int64_t)p * g.w + j_begin) * L.rec_words;
+
+    for (int j = j_begin; j < j_end; ++j, rec += L.rec_words) {
+        const int4 hdr = __ldg(reinterpret_cast<const int4 *>(rec));
+        const int2 *rowtab = reinterpret_cast<const int2 *>(rec + L.rowtab());
+        const int2 *evtab = reinterpret_cast<const int2 *>(rec + L.evtab());
+        const int2 *coltab = reinterpret_cast<const int2 *>(rec + L.coltab());
+        for (int q = threadIdx.x; q < g.hp; q += blockDim.x) {
+            const int k0 = q, k1 = q + g.hp;
+            const bool has1 = k1 < g.h;
+            const int2 t0 = __ldg(coltab + k0), t1 = __ldg(coltab + (has1 ? k1 : k0));
+            const int c0 = t0.x, c1 = t1.x;
+            const f32x2 w2 = pack2(__int_as_float(t0.y), __int_as_float(t1.y)), e2 = sub2(splat2(1.0f), w2);
+            const bool c00 = (unsigned)c0 < (unsigned)g.ph, c01 = (unsigned)(c0 + 1) < (unsigned)g.ph;
+            const bool c10 = has1 && (unsigned)c1 < (unsigned)g.ph, c11 = has1 && (unsigned)(c1 + 1) < (unsigned)g.ph;
+            float *ob = ob0 + (unsigned)(j * g.h);
+            if (hdr.y & 1) {
+                const int s_lo = __ldg(rowtab + ia).x - hdr.x, s_hi = __ldg(rowtab + ib - 1).x + 1 - hdr.x;
+                const bool rows_in = hdr.x + s_lo >= 0 && hdr.x + s_hi < g.pw;
+                const float *lo0 = opaque(pv0 + c0), *lo1 = opaque(pv0 + c1);
+                float *o0 = opaque(ob + k0), *o1 = opaque(ob + k1);
+                const bool hot = __all_sync(__activemask(), rows_in && has1 && c00 && c01 && c10 && c11);
+                if (hot) bp_march_plan<false>(evtab, s_lo, s_hi, lo0, lo1, o0, o1, plane, e2, w2, c00, c01, c10, c11, has1);
+                else bp_march_plan<true>(evtab, s_lo, s_hi, lo0, lo1, o0, o1, plane, e2, w2, c00, c01, c10, c11, has1);
+            } else {
+                float wq0, wq1, e0, e1;
+                unpack2(w2, wq0, wq1); unpack2(e2, e0, e1);
+                backproject_column_plan_checked(pv0 + c0, ob + k0, plane, rowtab, ia, ib, g.pw, g.ph, c00, c01, e0, wq0);
+                if (has1) backproject_column_plan_checked(pv0 + c1, ob + k1, plane, rowtab, ia, ib, g.pw, g.ph, c10, c11, e1, wq1);
+            }
+        }
     }
 }
 
@@ -586,17 +709,8 @@ static int fill_dims(BpDims &g, int B, int P, int pw, int ph, int d_total, int w
     g.hpw = (float)(pw - 1) / 2.0f; g.hph = (float)(ph - 1) / 2.0f;
     g.proj_view_stride = (int64_t)pw * ph;
     g.out_batch_stride = obs; g.out_chan_stride = ocs;
-    g.zero = 0.0f; g.tma_out = 0;
+    g.zero = 0.0f;
     return LR_OK;
-}
-
-#ifndef LR_BP_TMA_DEFAULT
-#define LR_BP_TMA_DEFAULT 0
-#endif
-static bool bp_tma_enabled() {      // LIFTREG_B200_BP_TMA=0/1 (kernel experiments); default: see DESIGN.md section 5
-    static int v = -1;
-    if (v < 0) { const char *e = getenv("LIFTREG_B200_BP_TMA"); v = e ? (e[0] == '1') : LR_BP_TMA_DEFAULT; }
-    return v != 0;
 }
 
 static int block_threads(int h) {
@@ -641,7 +755,10 @@ static dim3 forward_shape(BpDims &g, int n_views, unsigned &grid, int min_thread
     g.n_chunks = (g.d + g.ichunk - 1) / g.ichunk;
     g.n_views = n_views;
     g.n_vc = g.n_chunks * n_views * g.B;
-    g.js0 = 4; g.js1 = 2; g.js2 = 1;
+#ifndef LR_BP_JS0
+#define LR_BP_JS0 4
+#endif
+    g.js0 = LR_BP_JS0; g.js1 = LR_BP_JS0 / 2; g.js2 = LR_BP_JS0 / 4 > 0 ? LR_BP_JS0 / 4 : 1;
     // share of the short runs: about 1.2 waves of work, at most half (measured: 50/30/20 % is best at batch 1 = 0.9
     // waves of 4-row blocks on 6 resident blocks per SM, 90/8/2 % at batch 8)
     int f0 = f0_env, f1 = f1_env;
@@ -689,21 +806,61 @@ extern "C" int lr_backproject_forward_slab(const float *proj, const float *poses
             continue;
         }
         const dim3 block = forward_shape(g, np, grid, 32);
-        // output rows through shared memory + cp.async.bulk: needs 16-byte aligned rows everywhere
-        const size_t stage_bytes = sizeof(float) * (size_t)g.ichunk * h;
-        g.tma_out = bp_tma_enabled() && h % 4 == 0 && ((uintptr_t)out & 15) == 0 && out_batch_stride % 4 == 0 &&
-                    out_chan_stride % 4 == 0 && stage_bytes <= 96 * 1024;
-        if (g.tma_out) {
-            static thread_local size_t attr_set = 0;      // opt in above the 48 KB default once per thread / size
-            if (stage_bytes > 48 * 1024 && stage_bytes > attr_set) {
-                cudaFuncSetAttribute(backproject_forward_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-                attr_set = 96 * 1024;
-            }
-            backproject_forward_rows_kernel<true><<<grid, block, stage_bytes, as_stream(stream)>>>(proj, out, g, ps);
-        } else {
-            backproject_forward_rows_kernel<false><<<grid, block, 0, as_stream(stream)>>>(proj, out, g, ps);
-        }
+        backproject_forward_rows_kernel<<<grid, block, 0, as_stream(stream)>>>(proj, out, g, ps);
         if (int e = check_launch("backproject_forward_rows_kernel")) return e;
+    }
+    return LR_OK;
+}
+
+extern "C" size_t lr_backproject_plan_bytes(int P, int pw, int ph, int d_total, int w, int h) {
+    if (P <= 0 || pw <= 0 || ph <= 0 || d_total <= 0 || w <= 0 || h <= 0) return 0;
+    const BpPlanLayout L = plan_layout(d_total, h);
+    return sizeof(int) * (size_t)P * w * L.rec_words;
+}
+
+extern "C" int lr_backproject_plan_build(const float *poses, int P, int pw, int ph, int d_total, int w, int h, void *plan,
+                                         size_t plan_bytes, lr_stream_t stream) {
+    LR_REQUIRE(poses && plan, "backproject_plan_build: null pointer");
+    BpDims g;
+    if (int e = fill_dims(g, 1, P, pw, ph, d_total, w, h, 0, 0)) return e;
+    LR_REQUIRE(((uintptr_t)plan & 15) == 0, "backproject_plan_build: plan must be 16-byte aligned");
+    const size_t need = lr_backproject_plan_bytes(P, pw, ph, d_total, w, h);
+    if (plan_bytes < need) {
+        set_error("backproject_plan_build: plan buffer too small (%zu < %zu bytes)", plan_bytes, need);
+        return LR_ERR_WORKSPACE;
+    }
+    LR_REQUIRE(w <= 65535, "backproject_plan_build: w must be <= 65535 (grid limit)");
+    const BpPlanLayout L = plan_layout(d_total, h);
+    for (int p0 = 0; p0 < P; p0 += BP_MAX_VIEWS) {
+        const int np = P - p0 < BP_MAX_VIEWS ? P - p0 : BP_MAX_VIEWS;
+        BpPoses ps;
+        for (int q = 0; q < np; ++q)
+            for (int c = 0; c < 3; ++c) ps.s[q][c] = poses[(p0 + q) * 3 + c];
+        g.p0 = p0;
+        backproject_plan_kernel<<<dim3((unsigned)w, (unsigned)np), 256, 0, as_stream(stream)>>>((int *)plan, L, g, ps);
+        if (int e = check_launch("backproject_plan_kernel")) return e;
+    }
+    return LR_OK;
+}
+
+extern "C" int lr_backproject_forward_planned(const float *proj, const void *plan, int B, int P, int pw, int ph, int d_total,
+                                              int w, int h, int i_begin, int i_count, float *out,
+                                              int64_t out_batch_stride, int64_t out_chan_stride, lr_stream_t stream) {
+    LR_REQUIRE(proj && plan && out, "backproject_forward_planned: null pointer");
+    BpDims g;
+    if (int e = fill_dims(g, B, P, pw, ph, d_total, w, h, out_batch_stride, out_chan_stride, i_begin, i_count)) return e;
+    const int d = g.d;
+    LR_REQUIRE(out_chan_stride >= (int64_t)d * w * h, "backproject_forward_planned: out_chan_stride smaller than a volume");
+    LR_REQUIRE(((uintptr_t)plan & 15) == 0, "backproject_forward_planned: plan must be 16-byte aligned");
+    const BpPlanLayout L = plan_layout(d_total, h);
+    for (int p0 = 0; p0 < P; p0 += BP_MAX_VIEWS) {
+        const int np = P - p0 < BP_MAX_VIEWS ? P - p0 : BP_MAX_VIEWS;
+        g.p0 = p0;
+        unsigned grid;
+        LR_REQUIRE((int64_t)w * ((d + 3) / 4) * np * B < (1ll << 31), "backproject_forward_planned: too many blocks for one launch");
+        const dim3 block = forward_shape(g, np, grid);
+        backproject_forward_plan_kernel<<<grid, block, 0, as_stream(stream)>>>(proj, out, (const int *)plan, L, g);
+        if (int e = check_launch("backproject_forward_plan_kernel")) return e;
     }
     return LR_OK;
 }

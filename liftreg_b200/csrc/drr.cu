@@ -109,6 +109,7 @@ struct Taps {
     float wt[8];      // ATen order: tnw tne tsw tse bnw bne bsw bse (x fastest, then y, then z)
     int base;         // voxel offset of tap (z0,y0,x0); < 2^31 (checked on the host)
     int x0, y0, z0;
+    float wx1, wy1, wz1;   // fractional parts (upper-tap weights)
 };
 
 __device__ __forceinline__ Taps make_taps(const Sample &s, const DrrDims &g) {
@@ -124,6 +125,7 @@ __device__ __forceinline__ Taps make_taps(const Sample &s, const DrrDims &g) {
     t.wt[0] = mul_rn(a00, wz0); t.wt[1] = mul_rn(a10, wz0); t.wt[2] = mul_rn(a01, wz0); t.wt[3] = mul_rn(a11, wz0);
     t.wt[4] = mul_rn(a00, wz1); t.wt[5] = mul_rn(a10, wz1); t.wt[6] = mul_rn(a01, wz1); t.wt[7] = mul_rn(a11, wz1);
     t.base = (t.z0 * g.w + t.y0) * g.h + t.x0;
+    t.wx1 = wx1; t.wy1 = wy1; t.wz1 = wz1;
     return t;
 }
 
@@ -139,7 +141,23 @@ __device__ __forceinline__ unsigned taps_mask(const Taps &t, const DrrDims &g) {
     return (vz0 ? mxy : 0u) | ((vz1 ? mxy : 0u) << 4);
 }
 
+// One sample in the fast-numerics order (LR_NUMERICS_FAST): taps outside the volume enter as 0, the blend is seven fused
+// lerps (x, then y, then z) over the same floor indices and fractional weights.
+__device__ __forceinline__ float sample_lerp_masked(const float *__restrict__ b, unsigned m, int sy, int sz, float wx1, float wy1, float wz1) {
+    float v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const int off = (c & 1) + ((c >> 1) & 1) * sy + (c >> 2) * sz;
+        v[c] = ((m >> c) & 1u) ? __ldg(b + off) : 0.0f;
+    }
+    const float c00 = fma_rn(wx1, sub_rn(v[1], v[0]), v[0]), c10 = fma_rn(wx1, sub_rn(v[3], v[2]), v[2]);
+    const float c01 = fma_rn(wx1, sub_rn(v[5], v[4]), v[4]), c11 = fma_rn(wx1, sub_rn(v[7], v[6]), v[6]);
+    const float d0 = fma_rn(wy1, sub_rn(c10, c00), c00), d1 = fma_rn(wy1, sub_rn(c11, c01), c01);
+    return fma_rn(wz1, sub_rn(d1, d0), d0);
+}
+
 // One ray, scalar, boundary-safe: the general path (also used by rays whose pair partner is missing).
+template <bool FAST>
 __device__ __forceinline__ float march_ray(const float *__restrict__ V, const Ray &r, const DrrDims &g, int jlo, int jhi) {
     const int sy = g.h, sz = g.w * g.h;
     float acc = 0.0f;
@@ -152,10 +170,14 @@ __device__ __forceinline__ float march_ray(const float *__restrict__ V, const Ra
         if (m == 0u) continue;                                  // contributes exactly +0
         const float *b = V + t.base;
         float o = 0.0f;
+        if (FAST) {
+            o = sample_lerp_masked(b, m, sy, sz, t.wx1, t.wy1, t.wz1);
+        } else {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {                           // ATen: out += val*w per tap, separately rounded
-            const int off = (c & 1) + ((c >> 1) & 1) * sy + (c >> 2) * sz;
-            if ((m >> c) & 1u) o = add_rn(o, mul_rn(__ldg(b + off), t.wt[c]));
+            for (int c = 0; c < 8; ++c) {                       // ATen: out += val*w per tap, separately rounded
+                const int off = (c & 1) + ((c >> 1) & 1) * sy + (c >> 2) * sz;
+                if ((m >> c) & 1u) o = add_rn(o, mul_rn(__ldg(b + off), t.wt[c]));
+            }
         }
         acc = add_rn(acc, o);                                   // sum over the ray (sdct:81), j ascending
     }
@@ -179,6 +201,7 @@ __device__ __forceinline__ float finish_ray(float acc, const Ray &r, const DrrDi
 #ifndef LR_DRR_MINB
 #define LR_DRR_MINB 4
 #endif
+template <bool FAST>
 __global__ void __launch_bounds__(32 * DRR_PAIRS * DRR_SEGS, LR_DRR_MINB)
     drr_forward_kernel(const float *__restrict__ vol, float *__restrict__ proj, DrrDims g, DrrViews views) {
     __shared__ float2 part[DRR_SEGS][DRR_PAIRS][32];
@@ -197,8 +220,8 @@ __global__ void __launch_bounds__(32 * DRR_PAIRS * DRR_SEGS, LR_DRR_MINB)
     const int seg_lo = seg * g.seg_len, seg_hi = min(g.w, seg_lo + g.seg_len) - 1;   // this warp's run of planes
 
     if (!(ra.clipped && rb.clipped)) {          // unusual geometry (emitter inside the slab): scalar path only
-        acca = march_ray(V, ra, g, seg_lo, seg_hi);
-        accb = march_ray(V, rb, g, seg_lo, seg_hi);
+        acca = march_ray<FAST>(V, ra, g, seg_lo, seg_hi);
+        accb = march_ray<FAST>(V, rb, g, seg_lo, seg_hi);
     } else {
     const f32x2 zero = splat2(g.zero), one = splat2(1.0f), mone = splat2(-1.0f);
     const f32x2 Dx = pack2(ra.Dx, rb.Dx), Dy = pack2(ra.Dy, rb.Dy), Dz = pack2(ra.Dz, rb.Dz), r2 = pack2(ra.r2, rb.r2);
@@ -226,12 +249,7 @@ __global__ void __launch_bounds__(32 * DRR_PAIRS * DRR_SEGS, LR_DRR_MINB)
         floor2_fi(ix, fx, x0a, x0b);       // clipped rays stay within a few voxels of the volume: |x| << 2^22
         floor2_fi(iy, fy, y0a, y0b);
         floor2_fi(iz, fz, z0a, z0b);
-        const f32x2 wx1 = sub2(ix, fx), wx0 = sub2(add2(fx, one), ix);
-        const f32x2 wy1 = sub2(iy, fy), wy0 = sub2(add2(fy, one), iy);
-        const f32x2 wz1 = sub2(iz, fz), wz0 = sub2(add2(fz, one), iz);
-        const f32x2 a00 = mul2(wx0, wy0), a10 = mul2(wx1, wy0), a01 = mul2(wx0, wy1), a11 = mul2(wx1, wy1);
-        const f32x2 wt[8] = {mul2(a00, wz0), mul2(a10, wz0), mul2(a01, wz0), mul2(a11, wz0),
-                             mul2(a00, wz1), mul2(a10, wz1), mul2(a01, wz1), mul2(a11, wz1)};
+        const f32x2 wx1 = sub2(ix, fx), wy1 = sub2(iy, fy), wz1 = sub2(iz, fz);
         const bool ina = (unsigned)x0a < (unsigned)(g.h - 1) && (unsigned)y0a < (unsigned)(g.w - 1) && (unsigned)z0a < (unsigned)(g.d - 1);
         const bool inb = (unsigned)x0b < (unsigned)(g.h - 1) && (unsigned)y0b < (unsigned)(g.w - 1) && (unsigned)z0b < (unsigned)(g.d - 1);
         const int basea = (z0a * g.w + y0a) * g.h + x0a, baseb = (z0b * g.w + y0b) * g.h + x0b;
@@ -244,17 +262,26 @@ __global__ void __launch_bounds__(32 * DRR_PAIRS * DRR_SEGS, LR_DRR_MINB)
             val[2] = pack2(__ldg(pa1), __ldg(pb1)); val[3] = pack2(__ldg(pa1 + 1), __ldg(pb1 + 1));
             val[4] = pack2(__ldg(pa2), __ldg(pb2)); val[5] = pack2(__ldg(pa2 + 1), __ldg(pb2 + 1));
             val[6] = pack2(__ldg(pa3), __ldg(pb3)); val[7] = pack2(__ldg(pa3 + 1), __ldg(pb3 + 1));
-            f32x2 o = splat2(0.0f);
+            f32x2 o;
+            if (FAST) {       // seven fused lerps instead of 12 weight products + 8 products + 7 sums
+                const f32x2 c00 = fma2(wx1, sub2(val[1], val[0]), val[0]), c10 = fma2(wx1, sub2(val[3], val[2]), val[2]);
+                const f32x2 c01 = fma2(wx1, sub2(val[5], val[4]), val[4]), c11 = fma2(wx1, sub2(val[7], val[6]), val[6]);
+                const f32x2 d0 = fma2(wy1, sub2(c10, c00), c00), d1 = fma2(wy1, sub2(c11, c01), c01);
+                o = fma2(wz1, sub2(d1, d0), d0);
+            } else {
+                const f32x2 wx0 = sub2(add2(fx, one), ix), wy0 = sub2(add2(fy, one), iy), wz0 = sub2(add2(fz, one), iz);
+                const f32x2 a00 = mul2(wx0, wy0), a10 = mul2(wx1, wy0), a01 = mul2(wx0, wy1), a11 = mul2(wx1, wy1);
+                const f32x2 wt[8] = {mul2(a00, wz0), mul2(a10, wz0), mul2(a01, wz0), mul2(a11, wz0),
+                                     mul2(a00, wz1), mul2(a10, wz1), mul2(a01, wz1), mul2(a11, wz1)};
+                o = splat2(0.0f);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) o = add2(o, mul2_sep(val[c], wt[c], zero));   // ATen: out += val*w, no fma
+                for (int c = 0; c < 8; ++c) o = add2(o, mul2_sep(val[c], wt[c], zero));   // ATen: out += val*w, no fma
+            }
             float oa, ob;
             unpack2(o, oa, ob);
             acca = add_rn(acca, oa);                                                   // sum over the ray (sdct:81)
             accb = add_rn(accb, ob);
         } else {
-            float w_a[8], w_b[8];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) unpack2(wt[c], w_a[c], w_b[c]);
             const unsigned vxa0 = (unsigned)x0a < (unsigned)g.h, vxa1 = (unsigned)(x0a + 1) < (unsigned)g.h;
             const unsigned vya0 = (unsigned)y0a < (unsigned)g.w, vya1 = (unsigned)(y0a + 1) < (unsigned)g.w;
             const unsigned vza0 = (unsigned)z0a < (unsigned)g.d, vza1 = (unsigned)(z0a + 1) < (unsigned)g.d;
@@ -265,23 +292,37 @@ __global__ void __launch_bounds__(32 * DRR_PAIRS * DRR_SEGS, LR_DRR_MINB)
             const unsigned mxb = vxb0 | (vxb1 << 1), mxyb = (vyb0 ? mxb : 0u) | ((vyb1 ? mxb : 0u) << 2);
             const unsigned ma = (vza0 ? mxya : 0u) | ((vza1 ? mxya : 0u) << 4);
             const unsigned mb = (vzb0 ? mxyb : 0u) | ((vzb1 ? mxyb : 0u) << 4);
-            if (ma != 0u) {
-                float o = 0.0f;
+            if (FAST) {
+                float wxa, wxb, wya, wyb, wza, wzb;
+                unpack2(wx1, wxa, wxb); unpack2(wy1, wya, wyb); unpack2(wz1, wza, wzb);
+                if (ma != 0u) acca = add_rn(acca, sample_lerp_masked(V + basea, ma, (int)sy, (int)sz, wxa, wya, wza));
+                if (mb != 0u) accb = add_rn(accb, sample_lerp_masked(V + baseb, mb, (int)sy, (int)sz, wxb, wyb, wzb));
+            } else {
+                const f32x2 wx0 = sub2(add2(fx, one), ix), wy0 = sub2(add2(fy, one), iy), wz0 = sub2(add2(fz, one), iz);
+                const f32x2 a00 = mul2(wx0, wy0), a10 = mul2(wx1, wy0), a01 = mul2(wx0, wy1), a11 = mul2(wx1, wy1);
+                const f32x2 wt[8] = {mul2(a00, wz0), mul2(a10, wz0), mul2(a01, wz0), mul2(a11, wz0),
+                                     mul2(a00, wz1), mul2(a10, wz1), mul2(a01, wz1), mul2(a11, wz1)};
+                float w_a[8], w_b[8];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const int off = (c & 1) + ((c >> 1) & 1) * (int)sy + (c >> 2) * (int)sz;
-                    if ((ma >> c) & 1u) o = add_rn(o, mul_rn(__ldg(V + (basea + off)), w_a[c]));
-                }
-                acca = add_rn(acca, o);
-            }
-            if (mb != 0u) {
-                float o = 0.0f;
+                for (int c = 0; c < 8; ++c) unpack2(wt[c], w_a[c], w_b[c]);
+                if (ma != 0u) {
+                    float o = 0.0f;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const int off = (c & 1) + ((c >> 1) & 1) * (int)sy + (c >> 2) * (int)sz;
-                    if ((mb >> c) & 1u) o = add_rn(o, mul_rn(__ldg(V + (baseb + off)), w_b[c]));
+                    for (int c = 0; c < 8; ++c) {
+                        const int off = (c & 1) + ((c >> 1) & 1) * (int)sy + (c >> 2) * (int)sz;
+                        if ((ma >> c) & 1u) o = add_rn(o, mul_rn(__ldg(V + (basea + off)), w_a[c]));
+                    }
+                    acca = add_rn(acca, o);
                 }
-                accb = add_rn(accb, o);
+                if (mb != 0u) {
+                    float o = 0.0f;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const int off = (c & 1) + ((c >> 1) & 1) * (int)sy + (c >> 2) * (int)sz;
+                        if ((mb >> c) & 1u) o = add_rn(o, mul_rn(__ldg(V + (baseb + off)), w_b[c]));
+                    }
+                    accb = add_rn(accb, o);
+                }
             }
         }
     }
@@ -409,7 +450,8 @@ extern "C" int lr_drr_forward(const float *vol, int B, int d, int w, int h, cons
     return for_each_view_chunk(poses, n_pose_sets, B, P, [&](int n, const DrrViews &vs, int v0) {
         g.view0 = v0;
         dim3 grid((unsigned)((rh + 31) / 32), (unsigned)((rd + 2 * DRR_PAIRS - 1) / (2 * DRR_PAIRS)), (unsigned)n);
-        drr_forward_kernel<<<grid, dim3(32, DRR_PAIRS, DRR_SEGS), 0, as_stream(stream)>>>(vol, proj, g, vs);
+        if (numerics_mode() == LR_NUMERICS_FAST) drr_forward_kernel<true><<<grid, dim3(32, DRR_PAIRS, DRR_SEGS), 0, as_stream(stream)>>>(vol, proj, g, vs);
+        else drr_forward_kernel<false><<<grid, dim3(32, DRR_PAIRS, DRR_SEGS), 0, as_stream(stream)>>>(vol, proj, g, vs);
         return check_launch("drr_forward_kernel");
     });
 }

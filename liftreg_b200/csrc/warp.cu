@@ -17,6 +17,9 @@
 #ifndef LR_WARP_FWD_MINBLOCKS
 #define LR_WARP_FWD_MINBLOCKS 8      // 64 registers
 #endif
+#ifndef LR_WARP_FWD_MINBLOCKS_FAST
+#define LR_WARP_FWD_MINBLOCKS_FAST 10     // 51 registers: the single-channel lerp-form blend has fewer live values (8 blocks: 21.3 us, 10: 20.5)
+#endif
 #ifndef LR_WARP_BWD_MINBLOCKS
 #define LR_WARP_BWD_MINBLOCKS 6      // 80 registers
 #endif
@@ -344,7 +347,7 @@ __device__ __forceinline__ void warp_pair_fast(const float *__restrict__ src, fl
 // processed, so the HBM latency of the phi stream (the only compulsory traffic besides the store) is hidden behind a
 // whole plane of arithmetic instead of being exposed once per voxel.
 template <int PAD, int MODE, bool SCALE, bool IDENT, bool C1, bool FAST>
-__global__ void __launch_bounds__(WARP_TX * WARP_TY, LR_WARP_FWD_MINBLOCKS)   // 64 registers, 32 resident warps per SM
+__global__ void __launch_bounds__(WARP_TX * WARP_TY, (FAST && C1 && MODE == LR_MODE_LINEAR) ? LR_WARP_FWD_MINBLOCKS_FAST : LR_WARP_FWD_MINBLOCKS)
     warp_forward_kernel(const float *__restrict__ img, const float *__restrict__ phi, float *__restrict__ out, WarpDims g) {
     __shared__ IdentTable<WARP_TY * WARP_VY> ident;
     __shared__ float ident_z[WARP_NZ_MAX];
@@ -482,8 +485,8 @@ __global__ void __launch_bounds__(WARP_TX * WARP_TY)
 
 // d(warp)/d(phi) only, zeros padding: what a training step needs (the moving image is data, model :69).  Same
 // two-voxels-per-thread packed layout as the forward kernel.  The gradient is a gather, so it is deterministic; it is
-// evaluated in a factorised form (differences of x/y/z-adjacent taps times precomputed weight*grad products, with
-// fused multiply-adds), which differs from ATen's expression order by fp32 round-off only (tests: <= 2e-5 rel-L2).
+// evaluated as a tree of fused lerps over tap differences (24 packed operations for the three components), which
+// differs from ATen's expression order by fp32 round-off only (tests: <= 2e-5 rel-L2).
 template <bool SCALE>
 __device__ __forceinline__ void warp_bwd_phi_one(const float *__restrict__ gout_b, const float *__restrict__ img_b,
                                                  float *__restrict__ gp, const WarpDims &g, int vox, float ix, float iy,
@@ -524,10 +527,10 @@ __device__ __forceinline__ void warp_bwd_phi_one(const float *__restrict__ gout_
 }
 
 // One plane of d/dphi for the thread's two voxels; gz/gy/gx are the (identity-corrected) map values of (a, b).
-template <bool SCALE>
+template <bool SCALE, bool C1>
 __device__ __forceinline__ void warp_bwd_phi_pair(const float *__restrict__ gout_b, const float *__restrict__ img_b,
                                                   float *__restrict__ gp, const WarpDims &g, f32x2 gx, f32x2 gy, f32x2 gz,
-                                                  int voxa, int voxb, bool has_b) {
+                                                  int voxa, int voxb, bool has_b, f32x2 go_c1) {
     const f32x2 one = splat2(1.0f);
     const f32x2 ix = mul2(add2(gx, one), splat2(g.hx)), iy = mul2(add2(gy, one), splat2(g.hy)), iz = mul2(add2(gz, one), splat2(g.hz));
 
@@ -547,52 +550,50 @@ __device__ __forceinline__ void warp_bwd_phi_pair(const float *__restrict__ gout
         if (has_b) warp_bwd_phi_one<SCALE>(gout_b, img_b, gp, g, voxb, ixb, iyb, izb);
         return;
     }
-    const f32x2 wx1 = sub2(ix, fx), wx0 = sub2(add2(fx, one), ix);
-    const f32x2 wy1 = sub2(iy, fy), wy0 = sub2(add2(fy, one), iy);
-    const f32x2 wz1 = sub2(iz, fz), wz0 = sub2(add2(fz, one), iz);
+    const f32x2 wx1 = sub2(ix, fx), wy1 = sub2(iy, fy), wz1 = sub2(iz, fz);
     const bool la = x0a >= 0, ha = x0a < g.W - 1, lb = x0b >= 0, hb = x0b < g.W - 1;   // x taps inside?
+    const bool all_in = __all_sync(__activemask(), la && ha && lb && hb);                 // no lane masks a tap: plain loads
     const int a0 = z0a * g.HW + y0a * g.W + x0a, b0 = z0b * g.HW + y0b * g.W + x0b;      // signed: x0 may be -1
     const int a1 = a0 + g.W, a2 = a0 + g.HW, a3 = a2 + g.W;
     const int b1 = b0 + g.W, b2 = b0 + g.HW, b3 = b2 + g.W;
     f32x2 gix = splat2(0.0f), giy = splat2(0.0f), giz = splat2(0.0f);
 #pragma unroll 1
-    for (int c = 0; c < g.C; ++c) {
+    const int nchan = C1 ? 1 : g.C;
+    for (int c = 0; c < nchan; ++c) {
         const float *sc = opaque(img_b + (int64_t)c * g.nvox);
         const float *goc = gout_b + (int64_t)c * g.nvox_o;
-        // SCALE: d/dphi of 2*sample((img+1)/2) - 1.  The exact scalings by 2 (grad_out) and 1/2 (tap values) commute
-        // with every rounding below and cancel: use grad_out as it is and tap values img + 1.
-        const f32x2 go = pack2(ld_stream(goc + (unsigned)voxa), ld_stream(goc + (unsigned)voxb));
+        // SCALE: d/dphi of 2*sample((img+1)/2) - 1.  The exact scalings by 2 (grad_out) and 1/2 (tap values) cancel, and
+        // so does the "+1": the derivatives of the eight weights sum to zero.  The taps are used as they are; a tap that
+        // zeros padding skips has rescaled intensity 0, i.e. enters as -1.
+        // (single-channel images: grad_out of this plane was prefetched by the caller together with the map)
+        const f32x2 go = C1 ? go_c1 : pack2(ld_stream(goc + (unsigned)voxa), ld_stream(goc + (unsigned)voxb));
         const float *pa0 = sc + a0, *pa1 = sc + a1, *pa2 = sc + a2, *pa3 = sc + a3;
         const float *pb0 = sc + b0, *pb1 = sc + b1, *pb2 = sc + b2, *pb3 = sc + b3;
         f32x2 v[8];     // tap index t = tx + 2 ty + 4 tz
+        if (all_in) {
+            v[0] = pack2(__ldg(pa0), __ldg(pb0)); v[1] = pack2(__ldg(pa0 + 1), __ldg(pb0 + 1));
+            v[2] = pack2(__ldg(pa1), __ldg(pb1)); v[3] = pack2(__ldg(pa1 + 1), __ldg(pb1 + 1));
+            v[4] = pack2(__ldg(pa2), __ldg(pb2)); v[5] = pack2(__ldg(pa2 + 1), __ldg(pb2 + 1));
+            v[6] = pack2(__ldg(pa3), __ldg(pb3)); v[7] = pack2(__ldg(pa3 + 1), __ldg(pb3 + 1));
+        } else {
 #define LR_TAP(p, ok) ((ok) ? __ldg(p) : (SCALE ? -1.0f : 0.0f))
-        v[0] = pack2(LR_TAP(pa0, la), LR_TAP(pb0, lb)); v[1] = pack2(LR_TAP(pa0 + 1, ha), LR_TAP(pb0 + 1, hb));
-        v[2] = pack2(LR_TAP(pa1, la), LR_TAP(pb1, lb)); v[3] = pack2(LR_TAP(pa1 + 1, ha), LR_TAP(pb1 + 1, hb));
-        v[4] = pack2(LR_TAP(pa2, la), LR_TAP(pb2, lb)); v[5] = pack2(LR_TAP(pa2 + 1, ha), LR_TAP(pb2 + 1, hb));
-        v[6] = pack2(LR_TAP(pa3, la), LR_TAP(pb3, lb)); v[7] = pack2(LR_TAP(pa3 + 1, ha), LR_TAP(pb3 + 1, hb));
+            v[0] = pack2(LR_TAP(pa0, la), LR_TAP(pb0, lb)); v[1] = pack2(LR_TAP(pa0 + 1, ha), LR_TAP(pb0 + 1, hb));
+            v[2] = pack2(LR_TAP(pa1, la), LR_TAP(pb1, lb)); v[3] = pack2(LR_TAP(pa1 + 1, ha), LR_TAP(pb1 + 1, hb));
+            v[4] = pack2(LR_TAP(pa2, la), LR_TAP(pb2, lb)); v[5] = pack2(LR_TAP(pa2 + 1, ha), LR_TAP(pb2 + 1, hb));
+            v[6] = pack2(LR_TAP(pa3, la), LR_TAP(pb3, lb)); v[7] = pack2(LR_TAP(pa3 + 1, ha), LR_TAP(pb3 + 1, hb));
 #undef LR_TAP
-        if (SCALE) {
-#pragma unroll
-            for (int t = 0; t < 8; ++t) v[t] = add2(v[t], one);
         }
-        // d/dx: sum over (ty,tz) of (v[1,ty,tz] - v[0,ty,tz]) * wy*wz * go, and likewise for y and z.  The pairwise
-        // weight products are formed on the fly (keeping 12 more packed values live would cost occupancy).
-        const f32x2 wxs[2] = {wx0, wx1}, wys[2] = {wy0, wy1}, wzs[2] = {wz0, wz1};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int ty = q & 1, tz = q >> 1;
-            gix = fma2(sub2(v[1 + 2 * ty + 4 * tz], v[0 + 2 * ty + 4 * tz]), mul2(mul2(wys[ty], wzs[tz]), go), gix);
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int tx = q & 1, tz = q >> 1;
-            giy = fma2(sub2(v[tx + 2 + 4 * tz], v[tx + 4 * tz]), mul2(mul2(wxs[tx], wzs[tz]), go), giy);
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int tx = q & 1, ty = q >> 1;
-            giz = fma2(sub2(v[tx + 2 * ty + 4], v[tx + 2 * ty]), mul2(mul2(wxs[tx], wys[ty]), go), giz);
-        }
+        // The trilinear interpolant and its three partial derivatives as a tree of fused lerps (24 packed operations):
+        //   e = x-differences of the four (y,z) rows, c = x-lerps;  d/dx = lerp_z(lerp_y(e));
+        //   f = y-differences of c;  d/dy = lerp_z(f);  d/dz = lerp_y(c)(z1) - lerp_y(c)(z0)
+        const f32x2 e00 = sub2(v[1], v[0]), e10 = sub2(v[3], v[2]), e01 = sub2(v[5], v[4]), e11 = sub2(v[7], v[6]);
+        const f32x2 c00 = fma2(wx1, e00, v[0]), c10 = fma2(wx1, e10, v[2]), c01 = fma2(wx1, e01, v[4]), c11 = fma2(wx1, e11, v[6]);
+        const f32x2 ex0 = fma2(wy1, sub2(e10, e00), e00), ex1 = fma2(wy1, sub2(e11, e01), e01);
+        const f32x2 f0 = sub2(c10, c00), f1 = sub2(c11, c01);
+        const f32x2 d0 = fma2(wy1, f0, c00), d1 = fma2(wy1, f1, c01);
+        gix = fma2(go, fma2(wz1, sub2(ex1, ex0), ex0), gix);
+        giy = fma2(go, fma2(wz1, sub2(f1, f0), f0), giy);
+        giz = fma2(go, sub2(d1, d0), giz);
     }
     float ra, rb;
     unpack2(mul2(splat2(g.hz), giz), ra, rb);
@@ -606,7 +607,7 @@ __device__ __forceinline__ void warp_bwd_phi_pair(const float *__restrict__ gout
 // Same block shape and tapered z-blocking as the forward kernel: a run of consecutive planes per block, the map
 // values of plane z+1 fetched into registers before plane z is evaluated.  (With one plane per block the map and
 // grad_out loads sat at the head of every block with nothing to hide them: ncu long-scoreboard 7.3 warps per issue.)
-template <bool SCALE, bool IDENT>
+template <bool SCALE, bool IDENT, bool C1>
 __global__ void __launch_bounds__(WARP_TX * WARP_TY, LR_WARP_BWD_MINBLOCKS)
     warp_backward_phi_kernel(const float *__restrict__ gout, const float *__restrict__ img, const float *__restrict__ phi,
                              float *__restrict__ gphi, WarpDims g) {
@@ -643,13 +644,16 @@ __global__ void __launch_bounds__(WARP_TX * WARP_TY, LR_WARP_BWD_MINBLOCKS)
     }
     float cza = ld_stream(p0 + (unsigned)voxa), cya = ld_stream(p1 + (unsigned)voxa), cxa = ld_stream(p2 + (unsigned)voxa);
     float czb = ld_stream(p0 + (unsigned)voxb), cyb = ld_stream(p1 + (unsigned)voxb), cxb = ld_stream(p2 + (unsigned)voxb);
+    float cga = 0.f, cgb = 0.f;      // grad_out of the current plane (single-channel images only)
+    if (C1) { cga = ld_stream(gout_b + (unsigned)voxa); cgb = ld_stream(gout_b + (unsigned)voxb); }
 #pragma unroll 1
     for (int zi = 0; zi < nz; ++zi) {
-        float nza = 0.f, nya = 0.f, nxa = 0.f, nzb = 0.f, nyb = 0.f, nxb = 0.f;
-        if (zi + 1 < nz) {   // prefetch the next plane's map values
+        float nza = 0.f, nya = 0.f, nxa = 0.f, nzb = 0.f, nyb = 0.f, nxb = 0.f, nga = 0.f, ngb = 0.f;
+        if (zi + 1 < nz) {   // prefetch the next plane's map values (and grad_out: it comes from HBM like the map)
             const unsigned na = (unsigned)(voxa + g.HW), nb = (unsigned)(voxb + g.HW);
             nza = ld_stream(p0 + na); nya = ld_stream(p1 + na); nxa = ld_stream(p2 + na);
             nzb = ld_stream(p0 + nb); nyb = ld_stream(p1 + nb); nxb = ld_stream(p2 + nb);
+            if (C1) { nga = ld_stream(gout_b + na); ngb = ld_stream(gout_b + nb); }
         }
         f32x2 gx = pack2(cxa, cxb), gy = pack2(cya, cyb), gz = pack2(cza, czb);
         if (IDENT) {
@@ -657,8 +661,8 @@ __global__ void __launch_bounds__(WARP_TX * WARP_TY, LR_WARP_BWD_MINBLOCKS)
             gy = add2(gy, idy);
             gx = add2(gx, idx);
         }
-        warp_bwd_phi_pair<SCALE>(gout_b, img_b, gp, g, gx, gy, gz, voxa, voxb, has_b);
-        cza = nza; cya = nya; cxa = nxa; czb = nzb; cyb = nyb; cxb = nxb;
+        warp_bwd_phi_pair<SCALE, C1>(gout_b, img_b, gp, g, gx, gy, gz, voxa, voxb, has_b, pack2(cga, cgb));
+        cza = nza; cya = nya; cxa = nxa; czb = nzb; cyb = nyb; cxb = nxb; cga = nga; cgb = ngb;
         voxa += g.HW; voxb += g.HW;
     }
 }
@@ -882,13 +886,19 @@ extern "C" int lr_warp_backward_slab(const float *grad_out, const float *img, co
             forward_z_blocking(gz, nb);
             const dim3 grid2 = warp_grid(nb, gz.zblocks, H, W, WARP_VY);
             const dim3 blk(WARP_TX, WARP_TY);
+#define LR_LAUNCH_BWD_PHI(S, I)                                                                                              \
+    do {                                                                                                                     \
+        if (C == 1) warp_backward_phi_kernel<S, I, true><<<grid2, blk, 0, st>>>(grad_out + oo, img + io, phi + po, gp, gz);   \
+        else warp_backward_phi_kernel<S, I, false><<<grid2, blk, 0, st>>>(grad_out + oo, img + io, phi + po, gp, gz);         \
+    } while (0)
             if (sc) {
-                if (id) warp_backward_phi_kernel<true, true><<<grid2, blk, 0, st>>>(grad_out + oo, img + io, phi + po, gp, gz);
-                else warp_backward_phi_kernel<true, false><<<grid2, blk, 0, st>>>(grad_out + oo, img + io, phi + po, gp, gz);
+                if (id) LR_LAUNCH_BWD_PHI(true, true);
+                else LR_LAUNCH_BWD_PHI(true, false);
             } else {
-                if (id) warp_backward_phi_kernel<false, true><<<grid2, blk, 0, st>>>(grad_out + oo, img + io, phi + po, gp, gz);
-                else warp_backward_phi_kernel<false, false><<<grid2, blk, 0, st>>>(grad_out + oo, img + io, phi + po, gp, gz);
+                if (id) LR_LAUNCH_BWD_PHI(false, true);
+                else LR_LAUNCH_BWD_PHI(false, false);
             }
+#undef LR_LAUNCH_BWD_PHI
         } else if (padding == LR_PAD_ZEROS) launch_bwd<LR_PAD_ZEROS>(sc, id, grid, st, grad_out + oo, img + io, phi + po, gi, gp, g);
         else launch_bwd<LR_PAD_BORDER>(sc, id, grid, st, grad_out + oo, img + io, phi + po, gi, gp, g);
         if (int e = check_launch("warp_backward_kernel")) return e;

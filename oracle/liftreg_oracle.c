@@ -240,7 +240,8 @@ LRO_API void lro_drr_forward(const float *vol, int B, int d, int w, int h, const
                         float g[3];
                         ray_point(&r, j, d, w, h, y_mode, g);
                         /* flip (sdct:76): grid_sample x<-axis2 (W=h), y<-axis1 (H=w), z<-axis0 (D=d) */
-                        float s = sample3(V, d, w, h, g[2], g[1], g[0], 0, 0);
+                        float s = g_blend ? sample3_fast(V, d, w, h, g[2], g[1], g[0], 0, 0.0f)
+                                          : sample3(V, d, w, h, g[2], g[1], g[0], 0, 0);
                         if (samples && b == 0) samples[ray * w + j] = s;
                         acc_d += (double)s;
                         if (seg_len > 0) {

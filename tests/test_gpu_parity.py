@@ -789,3 +789,51 @@ def test_label_warp_mirror_of_mermaid_entry_point(dev):
     out01 = mermaid_utils.compute_warped_image_multiNC(cu(img, dev), cu(phi01, dev), spacing, spline_order=1,
                                                        zero_boundary=False, use_01_input=True)
     assert rel_l2(out01.cpu().numpy(), lin.cpu().numpy()) <= 1e-4       # coordinates round-trip through [0, 1] in fp32
+
+
+# ------------------------------------------------------------------ geometry plan
+@pytest.mark.parametrize("shape,pshape,B,P", [((160, 160, 160), (256, 256), 1, 4), ((33, 6, 70), (40, 31), 3, 2),
+                                              ((40, 9, 300), (64, 350), 1, 2), ((5, 7, 3), (9, 4), 2, 66), ((64, 48, 33), (20, 300), 1, 3)])
+def test_backproject_planned_equals_unplanned(dev, shape, pshape, B, P):
+    """lr_backproject_forward_planned (cached geometry tables) against
+    lr_backproject_forward (tables rebuilt in the kernel) in fast numerics: bit-identical, for the whole volume, for an
+    unaligned z-slab and through channel strides -- and both equal the oracle's fast blend order."""
+    import ctypes
+    from liftreg_b200 import _native, ops, synthetic
+    from oracle import c_oracle
+    lib = _native.lib()
+    prev = _native.set_numerics("fast")
+    try:
+        rs = np.random.RandomState(11)
+        d, w, h = shape
+        tp = cu(rs.uniform(-1, 1, (B, P) + pshape).astype(np.float32), dev)
+        poses = synthetic.wrapper_poses(60.0, P, shape[1]).astype(np.float32)
+        if P > 2:
+            poses[1, 1] = shape[1] * 1.02          # an emitter close to the volume: strong magnification, rows leave the detector
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        vp = lambda t: ctypes.c_void_p(t.data_ptr())
+        nv = d * w * h
+        ref = torch.empty((B, P, d, w, h), device=dev)
+        _native.check(lib.lr_backproject_forward(vp(tp), ops._fp(poses), B, P, pshape[0], pshape[1], d, w, h, vp(ref), P * nv, nv, st), "unplanned")
+        plan = ops.backproject_plan(poses, pshape, shape, dev)
+        out = torch.full((B, P + 2, d, w, h), 3.0, device=dev)            # channels 1..P of a wider buffer
+        view = out[:, 1:1 + P]
+        _native.check(lib.lr_backproject_forward_planned(vp(tp), vp(plan), B, P, pshape[0], pshape[1], d, w, h, 0, d,
+                                                         ctypes.c_void_p(view.data_ptr()), (P + 2) * nv, nv, st), "planned")
+        assert torch.equal(view, ref) and bool((out[:, 0] == 3.0).all()) and bool((out[:, -1] == 3.0).all())
+        if d >= 5:
+            z0, nz = d // 3, max(1, d // 2 - 1)
+            slab = torch.empty((B, P, nz, w, h), device=dev)
+            _native.check(lib.lr_backproject_forward_planned(vp(tp), vp(plan), B, P, pshape[0], pshape[1], d, w, h, z0, nz,
+                                                             vp(slab), P * nz * w * h, nz * w * h, st), "planned slab")
+            assert torch.equal(slab, ref[:, :, z0:z0 + nz])
+        if nv * B * P <= 4_000_000:
+            prev_blend = c_oracle.set_blend("fast")
+            try:
+                assert np.array_equal(ref.cpu().numpy(), c_oracle.backproject_forward(tp.cpu().numpy(), poses, shape))
+            finally:
+                c_oracle.set_blend(prev_blend)
+        assert torch.equal(ops.backproject(tp, poses, shape), ref)
+        assert ops.backproject_plan(poses, pshape, shape, dev).data_ptr() == plan.data_ptr()       # cached per geometry
+    finally:
+        _native.set_numerics(prev)
