@@ -308,6 +308,9 @@ __device__ __forceinline__ f32x2 bp_fetch_row(const float *lo0, const float *lo1
         const float a1 = (rv && c10) ? __ldg(q1) : 0.0f, b1 = (rv && c11) ? __ldg(q1 + 1) : 0.0f;
         va = pack2(a0, a1); vb = pack2(b0, b1);
     } else {
+#ifdef LR_BP_ABLATE_L1HIT       // experiment: every row fetch reads one of two detector rows (all L1 hits, same instruction stream)
+        roff = (roff & 1) * 256;
+#endif
         const float *q0 = lo0 + (unsigned)roff, *q1 = lo1 + (unsigned)roff;
         va = pack2(__ldg(q0), __ldg(q1)); vb = pack2(__ldg(q0 + 1), __ldg(q1 + 1));
     }
