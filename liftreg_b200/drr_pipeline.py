@@ -15,7 +15,8 @@ takes ~0.1 ms the loop is bound by the file system and PCIe, so here
 
 Slots form a ring of `depth` entries, so disk reads, PCIe copies, the kernel and disk writes of different cases overlap.
 File names, array shapes / dtypes and values are those of the reference loop (tests compare against the serial mirror
-calls).  `project_fn` lets the CPU tests inject the oracle as the compute stage; without it a CUDA device is mandatory.
+calls).  The compute stage is the CUDA one; `stage_factory` is the seam through which the CPU tests substitute a stage of
+their own (tests/pipeline_host_stage.py) -- the package itself ships no CPU path.
 """
 import os
 import queue
@@ -48,7 +49,7 @@ def _load_case(preprocessed_path, case_id, flip_axis1):
 
 
 def generate_drr_dataset(preprocessed_path, data_ids, drr_folder, scan_range=None, scan_num=None, geo_path=None,
-                         receptor_size=None, spacing=SPACING, flip_axis1=True, device="cuda", depth=3, project_fn=None,
+                         receptor_size=None, spacing=SPACING, flip_axis1=True, device="cuda", depth=3, stage_factory=None,
                          shard=None):
     """Writes `{id}_target_proj.npy`, `{id}_source_proj.npy` (float32 (P,rd,rh)) for every id and `poses.npy`
     (float64 (P,3)) into `drr_folder`; returns the poses.  See the module docstring for the pipeline.
@@ -71,8 +72,9 @@ def generate_drr_dataset(preprocessed_path, data_ids, drr_folder, scan_range=Non
     resolution = sdct._default_resolution(shape, receptor_size)
     P, (rd, rh) = poses.shape[0], (int(resolution[0]), int(resolution[1]))
 
-    if project_fn is not None:
-        stage = _HostStage(shape, P, rd, rh, depth, project_fn, poses, spacing)
+    # stage protocol: input_slot(slot) -> (2,d,w,h) host array; project(slot) -> token; wait_output(slot, token) -> (2,P,rd,rh)
+    if stage_factory is not None:
+        stage = stage_factory(shape, P, rd, rh, depth, poses, spacing)
     else:
         stage = _CudaStage(shape, P, rd, rh, depth, device, poses, spacing)
 
@@ -182,25 +184,4 @@ class _CudaStage:
 
     def wait_output(self, slot, token):
         token.synchronize()
-        return self.np_out[slot]
-
-
-class _HostStage:
-    """CPU test double of _CudaStage: `project_fn(mu (d,w,h) float32, poses, resolution, spacing) -> (P,rd,rh)`."""
-
-    def __init__(self, shape, P, rd, rh, depth, project_fn, poses, spacing):
-        self.fn, self.poses, self.res, self.spacing = project_fn, poses, (rd, rh), spacing
-        self.np_in = [np.empty((2,) + tuple(shape), np.float32) for _ in range(depth)]
-        self.np_out = [np.empty((2, P, rd, rh), np.float32) for _ in range(depth)]
-
-    def input_slot(self, slot):
-        return self.np_in[slot]
-
-    def project(self, slot):
-        for v in range(2):
-            mu = sdct.calc_relative_atten_coef(self.np_in[slot][v])
-            self.np_out[slot][v] = self.fn(mu, self.poses, self.res, self.spacing)
-        return None
-
-    def wait_output(self, slot, token):
         return self.np_out[slot]

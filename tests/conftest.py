@@ -28,6 +28,11 @@ def pytest_sessionstart(session):
         c_oracle.build()
     except Exception as e:  # pragma: no cover
         print("WARNING: could not build the C oracle: %r" % (e,))
+    try:        # the reference's own hot-path modules for the GPU box (git-ignored copy; no-op without /root/reference)
+        from oracle import vendor_reference
+        vendor_reference.vendor()
+    except Exception as e:  # pragma: no cover
+        print("WARNING: could not vendor the reference modules: %r" % (e,))
 
 
 def load_golden(name):

@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 
 from liftreg_b200 import drr_pipeline, sdct_projection_utils as sdct
+from pipeline_host_stage import host_stage
 
 
 def _make_dataset(root, n, shape, seed=7, dtype=np.float32):
@@ -31,7 +32,7 @@ def test_pipeline_host_stage_matches_serial_loop(tmp_path, depth):
     os.makedirs(pre)
     ids = _make_dataset(pre, 5, shape)
     poses = drr_pipeline.generate_drr_dataset(pre, ids, out, scan_range=60.0, scan_num=3, receptor_size=(14, 13), depth=depth,
-                                              project_fn=_oracle_project)
+                                              stage_factory=host_stage(_oracle_project))
     # poses.npy: sdct:139-155 (float64, voxel units), written once (:154)
     want_poses = sdct._wrapper_poses_scale(60.0, 3, 3.5) * shape[1]
     assert poses.dtype == np.float64 and np.array_equal(poses, want_poses)
@@ -59,7 +60,7 @@ def test_pipeline_geo_csv_default_detector_and_int16(tmp_path):
         seen.append((mu.dtype, tuple(resolution)))
         return _oracle_project(mu, poses, resolution, spacing)
 
-    poses = drr_pipeline.generate_drr_dataset(pre, ids, out, geo_path=str(geo), project_fn=fn)
+    poses = drr_pipeline.generate_drr_dataset(pre, ids, out, geo_path=str(geo), stage_factory=host_stage(fn))
     want = np.array([[-100.0, 46.2, -3.0], [0.0, 46.2, 0.0], [100.0, 46.2, 3.0]]) / (2.2, 2.2, 2.2)   # sdct:162-163
     assert np.array_equal(poses, want)
     assert all(dt == np.float32 and res == (12, 15) for dt, res in seen)      # int(1.5*d) x int(1.5*h), sdct:149-151
@@ -72,12 +73,12 @@ def test_pipeline_errors_surface(tmp_path):
     ids = _make_dataset(pre, 2, (6, 6, 6))
     np.save(os.path.join(pre, "case001_source.npy"), np.zeros((5, 6, 6), np.float32))     # shape mismatch inside the run
     with pytest.raises(ValueError):
-        drr_pipeline.generate_drr_dataset(pre, ids, out, scan_range=60.0, scan_num=2, project_fn=_oracle_project)
+        drr_pipeline.generate_drr_dataset(pre, ids, out, scan_range=60.0, scan_num=2, stage_factory=host_stage(_oracle_project))
     with pytest.raises(FileNotFoundError):
-        drr_pipeline.generate_drr_dataset(pre, ["missing"], out, scan_range=60.0, scan_num=2, project_fn=_oracle_project)
+        drr_pipeline.generate_drr_dataset(pre, ["missing"], out, scan_range=60.0, scan_num=2, stage_factory=host_stage(_oracle_project))
     with pytest.raises(ValueError):
-        drr_pipeline.generate_drr_dataset(pre, ids[:1], out, project_fn=_oracle_project)   # no geometry given
-    assert drr_pipeline.generate_drr_dataset(pre, [], out, scan_range=60.0, scan_num=2, project_fn=_oracle_project) is None
+        drr_pipeline.generate_drr_dataset(pre, ids[:1], out, stage_factory=host_stage(_oracle_project))   # no geometry given
+    assert drr_pipeline.generate_drr_dataset(pre, [], out, scan_range=60.0, scan_num=2, stage_factory=host_stage(_oracle_project)) is None
 
 
 @pytest.mark.gpu
@@ -105,7 +106,7 @@ def test_pipeline_case_sharding_covers_every_case_once(tmp_path):
     pre, out_a, out_b = str(tmp_path / "pre"), str(tmp_path / "a"), str(tmp_path / "b")
     os.makedirs(pre)
     ids = _make_dataset(pre, 5, shape)
-    kw = dict(scan_range=60.0, scan_num=2, receptor_size=(10, 11), project_fn=_oracle_project)
+    kw = dict(scan_range=60.0, scan_num=2, receptor_size=(10, 11), stage_factory=host_stage(_oracle_project))
     drr_pipeline.generate_drr_dataset(pre, ids, out_a, **kw)
     drr_pipeline.generate_drr_dataset(pre, ids, out_b, shard=(1, 3), **kw)
     assert sorted(os.listdir(out_b)) == sorted("%s_%s_proj.npy" % (i, k) for i in ids[1::3] for k in ("target", "source"))

@@ -109,6 +109,26 @@ def test_drr_csv_poses_and_anisotropic_spacing(dev):
     assert per_image_rel_l2(out, g["proj"]) <= TOL
 
 
+def test_calculate_projection_wraper_with_geo_csv_file(dev, tmp_path):
+    """sdct:161-177 executed end to end: emitter positions in mm from a CSV with a header line, divided by the spacing;
+    default detector int(1.5 d) x int(1.5 h); numpy in, numpy out."""
+    from liftreg_b200 import sdct_projection_utils as sdct
+    from oracle import c_oracle
+    g = load_golden("drr_small_csvposes")
+    spacing = tuple(float(s) for s in g["spacing"])
+    mm = g["poses"] * np.asarray(spacing)                                  # the CSV holds millimetres
+    geo = tmp_path / "geo.csv"
+    geo.write_text("x,y,z\n" + "\n".join(",".join(repr(float(v)) for v in row) for row in mm) + "\n")
+    proj, poses = sdct.calculate_projection_wraper_with_geo_csv_file(g["vol"], spacing, str(geo), receptor_size=(30, 30))
+    assert isinstance(proj, np.ndarray) and proj.dtype == np.float32 and proj.shape == g["proj"].shape
+    assert np.allclose(poses, g["poses"], rtol=1e-15, atol=0)
+    assert per_image_rel_l2(proj, g["proj"]) <= TOL                          # the reference's own output for these poses
+    assert np.array_equal(proj, c_oracle.drr_forward(g["vol"], poses, (30, 30), spacing, seg_len=c_oracle.kernel_seg_len(g["vol"].shape[1])))
+    d, _, h = g["vol"].shape                                                 # default detector: int(1.5 d) x int(1.5 h) (sdct:168-171)
+    proj2, _ = sdct.calculate_projection_wraper_with_geo_csv_file(g["vol"], spacing, str(geo))
+    assert proj2.shape == (poses.shape[0], int(d * 1.5), int(h * 1.5))
+
+
 def test_drr_cfg1_vs_reference_golden(dev):
     """BASELINE configs[0]: 160^3, 4 views / 60 deg, 240^2 detector, against the reference's CPU output."""
     from liftreg_b200 import sdct_projection_utils as sdct, synthetic
@@ -694,14 +714,23 @@ def test_pca_decode_backward_odd_k_uses_library_gemm(dev):
 # ------------------------------------------------------------------ BASELINE configs[2] / configs[4] shapes
 def test_cfg3_batch8_full_size_is_batch_independent(dev):
     """configs[2]: the hot-path ops of the full forward at 160^3, batch 8 (4 views, 256^2 detector).  Every batch item
-    must equal the batch-1 result of the same item, bit for bit, and item 0 must match the reference golden subset."""
-    from liftreg_b200 import ops, synthetic
+    must equal the batch-1 result of the same item, bit for bit, and item 0 -- whose inputs are the phantom, its
+    normalised DRRs and the smooth displacement the goldens were generated from -- must match the subsets the
+    reference itself produced (tests/golden/backproj_cfg2.npz, warp_cfg2.npz)."""
+    from liftreg_b200 import ops, synthetic, sdct_projection_utils as sdct
     shape, det, B, P = (160, 160, 160), (256, 256), 8, 4
     rs = np.random.RandomState(60)
-    poses = synthetic.wrapper_poses(60.0, P, shape[1]).astype(np.float32)
-    proj = torch.from_numpy(rs.uniform(-1, 1, (B, P) + det).astype(np.float32)).to(dev)
-    moving = torch.from_numpy(rs.uniform(-1, 1, (B, 1) + shape).astype(np.float32)).to(dev)
-    disp = torch.stack([torch.from_numpy(synthetic.smooth_displacement(shape, seed=s)) for s in range(B)]).to(dev)
+    poses = synthetic.wrapper_poses(60.0, P, shape[1])
+    hu = synthetic.ct_phantom(shape)
+    proj0 = synthetic.normalise_projection(sdct.calculate_projection(synthetic.hu_to_mu(hu), poses, det, [1, 1, 1], (2.2, 2.2, 2.2), dev))
+    proj_np = rs.uniform(-1, 1, (B, P) + det).astype(np.float32)
+    proj_np[0] = proj0
+    moving_np = rs.uniform(-1, 1, (B, 1) + shape).astype(np.float32)
+    moving_np[0, 0] = synthetic.hu_to_unit(hu)
+    poses = poses.astype(np.float32)
+    proj, moving = torch.from_numpy(proj_np).to(dev), torch.from_numpy(moving_np).to(dev)
+    disp = torch.stack([torch.from_numpy(synthetic.smooth_displacement(shape) if s == 0 else synthetic.smooth_displacement(shape, seed=s))
+                        for s in range(B)]).to(dev)
     x = torch.empty((B, 1 + P) + shape, device=dev)                      # the encoder's concat buffer (row f1)
     x[:, :1] = moving
     ops.backproject(proj, poses, shape, out=x, channel_offset=1)
@@ -711,6 +740,12 @@ def test_cfg3_batch8_full_size_is_batch_independent(dev):
         assert torch.equal(warped[b:b + 1], ops.warp(moving[b:b + 1], disp[b:b + 1], zero_boundary=True, using_scale=True,
                                                      disp_plus_identity=True))
     assert torch.equal(x[:, 0], moving[:, 0])
+    gb, gw = load_golden("backproj_cfg2"), load_golden("warp_cfg2")
+    lifted0, warped0 = x[0, 1:].cpu().numpy(), warped[0, 0].cpu().numpy()
+    for p in range(P):
+        assert rel_l2(lifted0[p, ::10, ::10, ::10], gb["out_sub"][0, p]) <= TOL
+        assert rel_l2(lifted0[p, 80, 80, :], gb["out_line"][p]) <= TOL
+    assert rel_l2(warped0[::8, ::8, ::8], gw["out_sub"]) <= TOL and rel_l2(warped0[80, 80, :], gw["out_line"]) <= TOL
 
 
 def test_cfg5_training_step_ops_batch4_forward_backward(dev):

@@ -45,7 +45,7 @@ def main():
     mu = torch.from_numpy(rs.uniform(0, 0.3, (1,) + VOL).astype(np.float32)).to(dev)
     sets = [dict(phi=phi.clone(), moving=moving.clone(), proj=proj.clone(), mu=mu.clone(),
                  warped=torch.empty((batch, 1) + VOL, device=dev), lifted=torch.empty((batch, P) + VOL, device=dev),
-                 drr=torch.empty((1, P, 240, 240), device=dev)) for _ in range(R)]
+                 drr=torch.empty((1, P, 240, 240), device=dev), drr256=torch.empty((1, P, 256, 256), device=dev)) for _ in range(R)]
     sp3 = np.array([2.2, 2.2, 2.2], np.float32)
     p64 = np.ascontiguousarray(poses, np.float64)
 
@@ -65,6 +65,10 @@ def main():
     def k_drr(s, st):
         _native.check(lib.lr_drr_forward(vp(s["mu"]), 1, *VOL, ops._dp(p64), 1, P, 240, 240, ops._fp(sp3), 0,
                                          ctypes.c_float(0.1), vp(s["drr"]), st), "drr")
+
+    def k_drr256(s, st):
+        _native.check(lib.lr_drr_forward(vp(s["mu"]), 1, *VOL, ops._dp(p64), 1, P, 256, 256, ops._fp(sp3), 0,
+                                         ctypes.c_float(0.1), vp(s["drr256"]), st), "drr256")
 
     gout = torch.from_numpy(rs.standard_normal((1, 1) + VOL).astype(np.float32)).to(dev)
     gphi = [torch.empty((1, 3) + VOL, device=dev) for _ in range(R)]
@@ -112,7 +116,8 @@ def main():
              "pca_bwd": (k_pca_bwd, 3 * nv, 4 * 3 * nv * 56 + 4 * 3 * nv), "warp_bwd": (k_warp_bwd, nv, 32 * nv),
              "drr_bwd": (k_drr_bwd, P * 240 * 240 * VOL[1], 4 * nv + 4 * P * 240 * 240), "backproject": (k_backproject, batch * P * nv, batch * (4 * P * nv + 4 * P * DET[0] * DET[1])),
              "backproject_planned": (k_backproject_planned, batch * P * nv, batch * (4 * P * nv + 4 * P * DET[0] * DET[1])),
-             "drr": (k_drr, P * 240 * 240 * VOL[1], 4 * nv + 4 * P * 240 * 240)}
+             "drr": (k_drr, P * 240 * 240 * VOL[1], 4 * nv + 4 * P * 240 * 240),
+             "drr256": (k_drr256, P * 256 * 256 * VOL[1], 4 * nv + 4 * P * 256 * 256)}
     for name in which:
         fn, n_units, nbytes = units[name]
         g = torch.cuda.CUDAGraph()
