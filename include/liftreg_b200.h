@@ -229,7 +229,8 @@ LR_API int lr_pca_decode(const float *coefs, const float *basis, const float *me
                          int add_identity, int D, int H, int W, float *out, lr_stream_t stream);
 
 /* adjoint wrt the coefficients (autograd of F.linear at model :102): grad_coefs (B,K) is ACCUMULATED into (caller
- * zero-initialises): grad_coefs[b,k] += sum_n grad_out[b,n] * basis[n,k].  K % 4 == 0, basis 16-byte aligned. */
+ * zero-initialises): grad_coefs[b,k] += sum_n grad_out[b,n] * basis[n,k].  K <= 160; K % 4 == 0 with 16-byte aligned
+ * basis / grad_out takes the TMA-pipelined path, anything else a scalar staging path. */
 LR_API int lr_pca_decode_backward(const float *grad_out, const float *basis, int B, int K, int64_t N,
                                   float *grad_coefs, lr_stream_t stream);
 

@@ -24,6 +24,7 @@ constexpr int DRR_ROWS = 4;         // detector rows (u) per block in the one-ra
 #define LR_DRR_SEGS 4
 #endif
 constexpr int DRR_PAIRS = LR_DRR_PAIRS;        // forward: ray pairs (2 detector rows each) per block along u
+static_assert(LR_DRR_SEGS >= 2, "the threads of the first two runs set up the block's rays");
 constexpr int DRR_SEGS = LR_DRR_SEGS;         // forward: every ray is cut into 4 runs of ceil(w/4) coronal planes, one warp each
 
 struct DrrView {
@@ -205,6 +206,7 @@ template <bool FAST>
 __global__ void __launch_bounds__(32 * DRR_PAIRS * DRR_SEGS, LR_DRR_MINB)
     drr_forward_kernel(const float *__restrict__ vol, float *__restrict__ proj, DrrDims g, DrrViews views) {
     __shared__ float2 part[DRR_SEGS][DRR_PAIRS][32];
+    __shared__ Ray rays[DRR_PAIRS][2][32];      // the block's rays, set up once (by the threads of the first two runs)
     const int v = blockIdx.x * 32 + threadIdx.x;
     const int ua = (blockIdx.y * DRR_PAIRS + threadIdx.y) * 2;
     const int seg = threadIdx.z;
@@ -212,12 +214,16 @@ __global__ void __launch_bounds__(32 * DRR_PAIRS * DRR_SEGS, LR_DRR_MINB)
     const bool has_b = ua + 1 < g.rd;
     float acca = 0.0f, accb = 0.0f;
     Ray ra, rb;
+    // ray_setup (two square roots, seven divisions) costs as much as ~2 marched samples; the DRR_SEGS threads that march
+    // the runs of one ray share one evaluation through shared memory instead of repeating it
+    if (live && seg < 2) rays[threadIdx.y][seg][threadIdx.x] = ray_setup(views.v[blockIdx.z], g, (seg == 1 && has_b) ? ua + 1 : ua, v);
+    __syncthreads();
     if (live) {
     const DrrView vw = views.v[blockIdx.z];
-    ra = ray_setup(vw, g, ua, v);
-    rb = ray_setup(vw, g, has_b ? ua + 1 : ua, v);
+    ra = rays[threadIdx.y][0][threadIdx.x];
+    rb = rays[threadIdx.y][1][threadIdx.x];
     const float *V = opaque(vol + (int64_t)vw.vol * g.nvox);
-    const int seg_lo = seg * g.seg_len, seg_hi = min(g.w, seg_lo + g.seg_len) - 1;   // this warp's run of planes
+    int seg_lo = seg * g.seg_len, seg_hi = min(g.w, seg_lo + g.seg_len) - 1;         // this warp's run of planes
 
     if (!(ra.clipped && rb.clipped)) {          // unusual geometry (emitter inside the slab): scalar path only
         acca = march_ray<FAST>(V, ra, g, seg_lo, seg_hi);
@@ -231,6 +237,14 @@ __global__ void __launch_bounds__(32 * DRR_PAIRS * DRR_SEGS, LR_DRR_MINB)
     const int ea = ra.j1 < ra.j0, eb = rb.j1 < rb.j0;
     int j0 = ea ? rb.j0 : (eb ? ra.j0 : min(ra.j0, rb.j0));
     int j1 = ea ? rb.j1 : (eb ? ra.j1 : max(ra.j1, rb.j1));
+    if (FAST) {
+        // Fixed runs of ceil(w/4) planes leave the warps of a block with very different amounts of work (a ray crosses
+        // the volume in a sub-range of the planes) and the finished ones wait at the block's barrier: 26 % of all warp
+        // stall samples (profiles/README.md round 2).  Fast numerics cuts the pair's CLIPPED range into equal runs
+        // instead; the fp32 sum is then taken in that run order (restated by the oracle: seg_len < 0).
+        const int n = j1 - j0 + 1, len = n > 0 ? (n + DRR_SEGS - 1) / DRR_SEGS : 1;
+        seg_lo = j0 + seg * len; seg_hi = seg_lo + len - 1;
+    }
     j0 = max(j0, seg_lo); j1 = min(j1, seg_hi);
 
     float jf = (float)j0;

@@ -315,12 +315,12 @@ __global__ void __launch_bounds__(PT_ROWS)
 // (k, row-group) accumulates its column over a quarter of the tile's rows for all batch items, partial sums stay in
 // registers across the block's tiles and are reduced once at the end (shared memory, then RED.ADD.F32: the summation
 // order across blocks is not fixed, results agree with a sequential sum to fp32 round-off).
-template <int BT>
+template <int BT, bool VEC>      // VEC: K % 4 == 0 and a 16-byte aligned basis (float4 staging); else scalar staging, odd pitch
 __global__ void __launch_bounds__(PD_ROWS)
     pca_decode_backward_kernel(const float *__restrict__ gout, const float *__restrict__ basis, float *__restrict__ gcoefs,
                                PcaDims g) {
     extern __shared__ float smem[];
-    const int pitch = pd_pitch(g.K);
+    const int pitch = VEC ? pd_pitch(g.K) : (g.K | 1);
     float *tile = smem;                                  // [PD_ROWS][pitch]
     float *gs = smem + (size_t)PD_ROWS * pitch;          // [PD_ROWS][BT] grad_out of the tile's rows
     const int tid = threadIdx.x;
@@ -339,23 +339,31 @@ __global__ void __launch_bounds__(PD_ROWS)
         const int64_t row0 = t * PD_ROWS;
         const int rows = (int)min((int64_t)PD_ROWS, g.N - row0);
         __syncthreads();
-        const float4 *src = reinterpret_cast<const float4 *>(basis + row0 * g.K);
-        const int n_f4 = rows * k4;
-        constexpr int UNR = 7;
-        for (int f0 = tid; f0 < tile_f4; f0 += UNR * PD_ROWS) {
-            float4 v[UNR];
+        if (VEC) {
+            const float4 *src = reinterpret_cast<const float4 *>(basis + row0 * g.K);
+            const int n_f4 = rows * k4;
+            constexpr int UNR = 7;
+            for (int f0 = tid; f0 < tile_f4; f0 += UNR * PD_ROWS) {
+                float4 v[UNR];
 #pragma unroll
-            for (int u = 0; u < UNR; ++u) {
-                const int f = f0 + u * PD_ROWS;
-                if (f < n_f4) v[u] = ld_stream4(src + f);
-            }
-#pragma unroll
-            for (int u = 0; u < UNR; ++u) {
-                const int f = f0 + u * PD_ROWS;
-                if (f < n_f4) {
-                    const int r = f / k4, kk = (f - r * k4) * 4;
-                    *reinterpret_cast<float4 *>(tile + r * pitch + kk) = v[u];
+                for (int u = 0; u < UNR; ++u) {
+                    const int f = f0 + u * PD_ROWS;
+                    if (f < n_f4) v[u] = ld_stream4(src + f);
                 }
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) {
+                    const int f = f0 + u * PD_ROWS;
+                    if (f < n_f4) {
+                        const int r = f / k4, kk = (f - r * k4) * 4;
+                        *reinterpret_cast<float4 *>(tile + r * pitch + kk) = v[u];
+                    }
+                }
+            }
+        } else {
+            const float *src = basis + row0 * g.K;
+            for (int f = tid; f < rows * g.K; f += PD_ROWS) {
+                const int r = f / g.K;
+                tile[r * pitch + (f - r * g.K)] = ld_stream(src + f);
             }
         }
 #pragma unroll
@@ -513,7 +521,7 @@ __global__ void __launch_bounds__(PT_ROWS)
 
 template <int BT>
 static int launch_pca_bwd(const float *gout, const float *basis, float *gcoefs, const PcaDims &g, cudaStream_t st) {
-    if (pca_tma_enabled() && g.N % 4 == 0 && ((uintptr_t)gout & 15) == 0 && g.K <= PT_ROWS) {
+    if (pca_tma_enabled() && g.K % 4 == 0 && ((uintptr_t)basis & 15) == 0 && g.N % 4 == 0 && ((uintptr_t)gout & 15) == 0 && g.K <= PT_ROWS) {
         const size_t smem_t = sizeof(float) * (size_t)PT_STAGES * ((size_t)PT_ROWS * g.K + (size_t)BT * PT_ROWS);
         if (smem_t <= 110 * 1024) {
             static thread_local bool attr_done = false;
@@ -531,14 +539,16 @@ static int launch_pca_bwd(const float *gout, const float *basis, float *gcoefs, 
             return check_launch("pca_decode_backward_tma_kernel");
         }
     }
-    const size_t tile = (size_t)PD_ROWS * pd_pitch(g.K);
+    const bool vec = g.K % 4 == 0 && ((uintptr_t)basis & 15) == 0;
+    const size_t tile = (size_t)PD_ROWS * (vec ? pd_pitch(g.K) : (g.K | 1));
     size_t smem_f = tile + (size_t)PD_ROWS * BT;
     const size_t red = (size_t)(PD_ROWS / 32 + 1) * g.K * BT;
     if (red > tile) smem_f += red - tile;
     const size_t smem = sizeof(float) * smem_f;
     if (smem > 200 * 1024) { set_error("pca_decode_backward: needs %zu bytes of shared memory", smem); return LR_ERR_BAD_ARGUMENT; }
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(pca_decode_backward_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaError_t e = vec ? cudaFuncSetAttribute(pca_decode_backward_kernel<BT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)
+                            : cudaFuncSetAttribute(pca_decode_backward_kernel<BT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) { set_error("pca_decode_backward: cannot raise shared memory limit: %s", cudaGetErrorString(e)); return LR_ERR_CUDA; }
     }
     int blocks_per_sm = (int)((220 * 1024) / (smem + 1024));
@@ -546,7 +556,8 @@ static int launch_pca_bwd(const float *gout, const float *basis, float *gcoefs, 
     if (blocks_per_sm < 1) blocks_per_sm = 1;
     int64_t grid = (int64_t)148 * blocks_per_sm;
     if (grid > g.n_tiles) grid = g.n_tiles;
-    pca_decode_backward_kernel<BT><<<(unsigned)grid, PD_ROWS, smem, st>>>(gout, basis, gcoefs, g);
+    if (vec) pca_decode_backward_kernel<BT, true><<<(unsigned)grid, PD_ROWS, smem, st>>>(gout, basis, gcoefs, g);
+    else pca_decode_backward_kernel<BT, false><<<(unsigned)grid, PD_ROWS, smem, st>>>(gout, basis, gcoefs, g);
     return check_launch("pca_decode_backward_kernel");
 }
 
@@ -558,8 +569,7 @@ extern "C" int lr_pca_decode_backward(const float *grad_out, const float *basis,
                                       lr_stream_t stream) {
     LR_REQUIRE(grad_out && basis && grad_coefs, "pca_decode_backward: null pointer");
     LR_REQUIRE(B > 0 && K > 0 && N > 0, "pca_decode_backward: non-positive dimension (B=%d K=%d N=%lld)", B, K, (long long)N);
-    LR_REQUIRE(K % 4 == 0 && K <= 160 && ((uintptr_t)basis & 15) == 0,
-               "pca_decode_backward: K must be a multiple of 4, <= 160, and the basis 16-byte aligned (got K=%d)", K);
+    LR_REQUIRE(K <= 160, "pca_decode_backward: K must be <= 160 (got %d)", K);
     PcaDims g;
     g.K = K; g.N = N; g.add_identity = 0; g.D = g.H = g.W = 0; g.nvox = 1; g.sp0 = g.sp1 = g.sp2 = 0.0;
     g.n_tiles = (N + PD_ROWS - 1) / PD_ROWS;

@@ -368,8 +368,6 @@ class _PcaDecode(torch.autograd.Function):
         grad_out = _need_cuda_f32(grad_out, "grad_out")
         B, N = grad_out.shape
         K = basis.shape[1]
-        if K % 4 != 0 or basis.data_ptr() % 16 != 0:
-            return grad_out @ basis, None, None, None, None, None, None      # odd K: library GEMM
         gcoefs = torch.zeros((B, K), device=grad_out.device, dtype=torch.float32)
         with torch.cuda.device(grad_out.device):
             _native.check(_native.lib().lr_pca_decode_backward(_ptr(grad_out), _ptr(basis), B, K, N, _ptr(gcoefs), _stream()),

@@ -100,6 +100,11 @@ DRR_SEGS = 4    # liftreg_b200/csrc/drr.cu DRR_SEGS: the kernel sums each ray in
 
 
 def kernel_seg_len(w):
+    """seg_len argument of drr_forward that reproduces the CUDA kernel's ray-sum order in the current blend mode:
+    exact numerics: DRR_SEGS fixed runs of ceil(w / DRR_SEGS) planes; fast numerics (set_blend('fast')): DRR_SEGS equal
+    runs over each ray pair's clipped range (negative value = number of balanced runs)."""
+    if lib().lro_get_blend():
+        return -DRR_SEGS
     return (int(w) + DRR_SEGS - 1) // DRR_SEGS
 
 

@@ -224,6 +224,32 @@ LRO_API void lro_project_grid(const double *poses, int P, int rd, int rh, int d,
 /* vol (B,d,w,h); proj (B,P,rd,rh); samples (optional, B==1 only): (P,rd,rh,w) pre-sum values.
  * proj = ((sum_j sample) * dx) * out_scale   -- sdct:81,85
  * seg_len > 0: the ray is summed in runs of seg_len planes, run sums added in run order (fp32). */
+/* The CUDA kernel's conservative clip of a ray to the coronal planes [j0, j1] in which it can touch the volume
+ * (liftreg_b200/csrc/drr.cu ray_setup; samples outside contribute exactly +0 in the reference).  Restated only because
+ * the fast-numerics kernel cuts each ray pair's clipped range into equal runs (seg_len < 0 below): the run boundaries,
+ * and with them the fp32 summation order, depend on it.  Same fp32 expressions in the same order. */
+static inline void kernel_ray_clip(const lro_ray *r, int u, int v, int rd, int rh, int d, int w, int h, int *j0, int *j1) {
+    float half_rd = (float)((double)rd / 2.0), half_rh = (float)((double)rh / 2.0);
+    float lx = (float)u - half_rd, lz = (float)v - half_rh;
+    float lim_x = d > 1 ? (float)d / 2.0f + 2.0f + (float)d / (float)(d - 1) : 3.0e38f;
+    float lim_z = h > 1 ? (float)h / 2.0f + 2.0f + (float)h / (float)(h - 1) : 3.0e38f;
+    float t0 = 0.0f, t1 = (float)(w - 1);
+    float inv_sy = 1.0f / r->sy;
+    float bx = (r->sx - lx) * inv_sy, bz = (r->sz - lz) * inv_sy;
+    if (fabsf(bx) > 1e-12f) {
+        float a = (-lim_x - lx) / bx, b = (lim_x - lx) / bx;
+        t0 = fmaxf(t0, fminf(a, b)); t1 = fminf(t1, fmaxf(a, b));
+    } else if (fabsf(lx) > lim_x) t1 = -1.0f;
+    if (fabsf(bz) > 1e-12f) {
+        float a = (-lim_z - lz) / bz, b = (lim_z - lz) / bz;
+        t0 = fmaxf(t0, fminf(a, b)); t1 = fminf(t1, fmaxf(a, b));
+    } else if (fabsf(lz) > lim_z) t1 = -1.0f;
+    *j0 = (int)floorf(t0) - 1; if (*j0 < 0) *j0 = 0;
+    *j1 = (int)ceilf(t1) + 1; if (*j1 > w - 1) *j1 = w - 1;
+    if (!(t1 >= t0)) { *j0 = 0; *j1 = -1; }
+    if (!(r->sy > (float)(w - 1))) { *j0 = 0; *j1 = w - 1; }     /* emitter inside the slab: no clipping */
+}
+
 LRO_API void lro_drr_forward(const float *vol, int B, int d, int w, int h, const double *poses, int P,
                              int rd, int rh, const float *spacing, int y_mode, float out_scale,
                              int acc64, int seg_len, float *proj, float *samples) {
@@ -236,6 +262,24 @@ LRO_API void lro_drr_forward(const float *vol, int B, int d, int w, int h, const
                     lro_ray r = ray_setup(poses + 3 * p, u, v, rd, rh, spacing);
                     size_t ray = ((size_t)p * rd + u) * rh + v;
                     float acc = 0.0f, run = 0.0f; double acc_d = 0.0;
+                    /* seg_len < 0: -seg_len balanced runs over the clipped range of the ray PAIR (u & ~1, u | 1) -- the
+                     * fast-numerics kernel's order; rays of an unclipped view keep fixed runs of ceil(w / -seg_len) */
+                    int bal = 0, bj0 = 0, blen = 1, fixed_len = seg_len;
+                    if (seg_len < 0) {
+                        int nseg = -seg_len;
+                        fixed_len = (w + nseg - 1) / nseg;
+                        if (r.sy > (float)(w - 1)) {
+                            int ua = u & ~1, ub = (ua + 1 < rd) ? ua + 1 : ua, a0, a1, b0, b1;
+                            lro_ray qa = ray_setup(poses + 3 * p, ua, v, rd, rh, spacing), qb = ray_setup(poses + 3 * p, ub, v, rd, rh, spacing);
+                            kernel_ray_clip(&qa, ua, v, rd, rh, d, w, h, &a0, &a1);
+                            kernel_ray_clip(&qb, ub, v, rd, rh, d, w, h, &b0, &b1);
+                            int ea = a1 < a0, eb = b1 < b0;
+                            int j0 = ea ? b0 : (eb ? a0 : (a0 < b0 ? a0 : b0));
+                            int j1 = ea ? b1 : (eb ? a1 : (a1 > b1 ? a1 : b1));
+                            int n = j1 - j0 + 1;
+                            bal = 1; bj0 = j0; blen = n > 0 ? (n + nseg - 1) / nseg : 1;
+                        }
+                    }
                     for (int j = 0; j < w; ++j) {
                         float g[3];
                         ray_point(&r, j, d, w, h, y_mode, g);
@@ -244,9 +288,12 @@ LRO_API void lro_drr_forward(const float *vol, int B, int d, int w, int h, const
                                           : sample3(V, d, w, h, g[2], g[1], g[0], 0, 0);
                         if (samples && b == 0) samples[ray * w + j] = s;
                         acc_d += (double)s;
-                        if (seg_len > 0) {
+                        if (bal) {                /* runs [bj0 + k*blen, bj0 + (k+1)*blen) */
                             run += s;
-                            if ((j + 1) % seg_len == 0 || j == w - 1) { acc += run; run = 0.0f; }
+                            if ((j >= bj0 && (j - bj0 + 1) % blen == 0) || j == w - 1) { acc += run; run = 0.0f; }
+                        } else if (fixed_len > 0) {
+                            run += s;
+                            if ((j + 1) % fixed_len == 0 || j == w - 1) { acc += run; run = 0.0f; }
                         } else {
                             acc += s;
                         }

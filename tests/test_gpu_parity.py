@@ -701,7 +701,8 @@ def test_pca_decode_backward_vs_float64(dev, B, K, N):
     assert rel_l2(coefs.grad.cpu().numpy(), want) <= GRAD_TOL
 
 
-def test_pca_decode_backward_odd_k_uses_library_gemm(dev):
+def test_pca_decode_backward_odd_k_native_scalar_path(dev):
+    """K % 4 != 0: the scalar-staging kernel (no library GEMM on the path)."""
     from liftreg_b200 import ops
     rs = np.random.RandomState(53)
     basis = cu((rs.standard_normal((300, 7)) * 1e-2).astype(np.float32), dev)
