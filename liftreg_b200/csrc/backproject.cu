@@ -51,7 +51,14 @@ struct BpDims {
     int64_t proj_view_stride;      // pw*ph
     int64_t out_batch_stride, out_chan_stride;
     float zero;                    // +0.0f the compiler cannot constant-fold (see mul2_sep)
+    // forward: ceil(2^32 / divisor) for the block-index decode (exact while grid * divisor < 2^32; 0 = plain division)
+    unsigned m_nj0, m_nj1, m_nj2, m_chunks, m_views;
 };
+
+// x / d for 0 <= x with a precomputed magic = ceil(2^32 / d) (0: divide; d == 1 has no 32-bit magic either)
+__device__ __forceinline__ int div_magic(int x, int d, unsigned magic) {
+    return magic ? (int)__umulhi((unsigned)x, magic) : x / d;
+}
 
 struct AxisTap {      // one axis of the bilinear footprint
     int i0;           // floor index (may be out of range)
@@ -296,12 +303,15 @@ struct __align__(8) BpEvent {
     int roff;
 };
 
-template <bool CHK>
+// One detector row for the thread's two columns: T = fma(P[r][c+1], wq, P[r][c] * e).  ROWCHK: the row may lie outside
+// the detector (roff < 0: T is exactly +0, zeros padding) -- a warp-uniform test, so a branch; COLCHK: taps of this
+// thread's columns may lie outside (per-lane predicates).
+template <bool ROWCHK, bool COLCHK>
 __device__ __forceinline__ f32x2 bp_fetch_row(const float *lo0, const float *lo1, int roff, f32x2 e2, f32x2 w2, bool c00,
                                               bool c01, bool c10, bool c11) {
     f32x2 va, vb;
-    if (CHK) {
-        const bool rv = roff >= 0;
+    if (COLCHK) {
+        const bool rv = !ROWCHK || roff >= 0;
         const unsigned o = rv ? (unsigned)roff : 0u;
         const float *q0 = lo0 + o, *q1 = lo1 + o;
         const float a0 = (rv && c00) ? __ldg(q0) : 0.0f, b0 = (rv && c01) ? __ldg(q0 + 1) : 0.0f;
@@ -311,8 +321,13 @@ __device__ __forceinline__ f32x2 bp_fetch_row(const float *lo0, const float *lo1
 #ifdef LR_BP_ABLATE_L1HIT       // experiment: every row fetch reads one of two detector rows (all L1 hits, same instruction stream)
         roff = (roff & 1) * 256;
 #endif
-        const float *q0 = lo0 + (unsigned)roff, *q1 = lo1 + (unsigned)roff;
+        // ROWCHK: a row outside the detector is fetched from row 0 instead and its T replaced by +0 afterwards -- two
+        // selects, no branch: a branch here would keep the compiler from batching the loads of the unrolled rows
+        const unsigned o = ROWCHK ? (unsigned)max(roff, 0) : (unsigned)roff;
+        const float *q0 = lo0 + o, *q1 = lo1 + o;
         va = pack2(__ldg(q0), __ldg(q1)); vb = pack2(__ldg(q0 + 1), __ldg(q1 + 1));
+        const f32x2 t = fma2(vb, w2, mul2(va, e2));
+        return (ROWCHK && roff < 0) ? 0ull : t;
     }
     return fma2(vb, w2, mul2(va, e2));
 }
@@ -330,21 +345,21 @@ __device__ __forceinline__ f32x2 bp_fetch_row(const float *lo0, const float *lo1
 #endif
 
 // One thread's two columns over one sub-chunk of planes.
-template <bool CHK>
+template <bool ROWCHK, bool COLCHK>
 __device__ __forceinline__ void bp_march_rows(const BpEvent *__restrict__ ev, int s_lo, int s_hi, const float *lo0,
                                               const float *lo1, float *o0, float *o1, unsigned ofs, unsigned step,
                                               f32x2 e2, f32x2 w2, bool c00, bool c01, bool c10, bool c11, bool has1) {
-    f32x2 t_prev = bp_fetch_row<CHK>(lo0, lo1, ev[s_lo].roff, e2, w2, c00, c01, c10, c11);
+    f32x2 t_prev = bp_fetch_row<ROWCHK, COLCHK>(lo0, lo1, ev[s_lo].roff, e2, w2, c00, c01, c10, c11);
     LR_BP_UNROLL_PRAGMA
     for (int s = s_lo + 1; s <= s_hi; ++s) {
         const BpEvent e = ev[s];
-        const f32x2 t = bp_fetch_row<CHK>(lo0, lo1, e.roff, e2, w2, c00, c01, c10, c11);
+        const f32x2 t = bp_fetch_row<ROWCHK, COLCHK>(lo0, lo1, e.roff, e2, w2, c00, c01, c10, c11);
         if (e.n >= 0.0f) {
             const f32x2 n2 = splat2(e.n), s2 = splat2(sub_rn(1.0f, e.n));
             float r0v, r1v;
             unpack2(fma2(t, n2, mul2(t_prev, s2)), r0v, r1v);
             st_stream(o0 + ofs, r0v);
-            if (!CHK || has1) st_stream(o1 + ofs, r1v);
+            if (!COLCHK || has1) st_stream(o1 + ofs, r1v);
             ofs += step;
         }
         t_prev = t;
@@ -361,13 +376,14 @@ __global__ void LR_BP_ROWS_BOUNDS
 
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
     int L = blockIdx.x, nj = g.nj0, js = g.js0, j_base = 0;      // block index -> (run of rows, chunk, view, batch item)
+    unsigned m_nj = g.m_nj0;
     if (L >= g.nj0 * g.n_vc) {
-        L -= g.nj0 * g.n_vc; nj = g.nj1; js = g.js1; j_base = g.nj0 * g.js0;
-        if (L >= g.nj1 * g.n_vc) { L -= g.nj1 * g.n_vc; nj = g.nj2; js = g.js2; j_base += g.nj1 * g.js1; }
+        L -= g.nj0 * g.n_vc; nj = g.nj1; js = g.js1; j_base = g.nj0 * g.js0; m_nj = g.m_nj1;
+        if (L >= g.nj1 * g.n_vc) { L -= g.nj1 * g.n_vc; nj = g.nj2; js = g.js2; j_base += g.nj1 * g.js1; m_nj = g.m_nj2; }
     }
-    const int vc = L / nj;
-    const int bv = vc / g.n_chunks;
-    const int bi = bv / g.n_views;
+    const int vc = div_magic(L, nj, m_nj);              // (three integer divisions were a third of the block prologue)
+    const int bv = div_magic(vc, g.n_chunks, g.m_chunks);
+    const int bi = div_magic(bv, g.n_views, g.m_views);
     const int pl = bv - bi * g.n_views;
     const int p = g.p0 + pl;
     const int i_begin = (vc - bv * g.n_chunks) * g.ichunk;
@@ -396,6 +412,7 @@ __global__ void LR_BP_ROWS_BOUNDS
                 const int r_last = __shfl_sync(0xffffffffu, r0, i_count - 1);
                 const bool mono = lane == 0 || !act || r0 > r_prev;
                 const bool fast = __all_sync(0xffffffffu, mono) && (r_last + 1 - r_base < BP_EV_MAX);
+                const int r_sub_last = __shfl_sync(0xffffffffu, r0, min((lane / g.isub) * g.isub + g.isub - 1, i_count - 1));
                 if (act) {
                     BpRow r;
                     r.off0 = r0 * g.ph; r.n = t.w1; r.s = sub_rn(1.0f, t.w1);
@@ -412,7 +429,8 @@ __global__ void LR_BP_ROWS_BOUNDS
                         BpEvent e; e.n = t.w1; e.roff = (unsigned)(r0 + 1) < (unsigned)g.pw ? (r0 + 1) * g.ph : -1;
                         ev[slot] = e;
                         const int sub = lane / g.isub, rem = lane - sub * g.isub;
-                        if (rem == 0) sub_lo[jr][sub] = slot - 1;
+                        // bit 30 of the first slot: every detector row of this sub-chunk lies inside the detector
+                        if (rem == 0) sub_lo[jr][sub] = (slot - 1) | ((r0 >= 0 && r_sub_last + 1 < g.pw) ? (1 << 30) : 0);
                         if (rem == g.isub - 1 || lane == i_count - 1) sub_hi[jr][sub] = slot;
                     }
                 }
@@ -452,14 +470,20 @@ __global__ void LR_BP_ROWS_BOUNDS
             const bool c10 = has1 && (unsigned)c1 < (unsigned)g.ph, c11 = has1 && (unsigned)(c1 + 1) < (unsigned)g.ph;
             float *ob = ob0 + (unsigned)(j * g.h);
             if (fl & 1) {
-                const int s_lo = sub_lo[jr][threadIdx.y], s_hi = sub_hi[jr][threadIdx.y];
+                const int s_lo_f = sub_lo[jr][threadIdx.y], s_lo = s_lo_f & ((1 << 30) - 1), s_hi = sub_hi[jr][threadIdx.y];
+                // (block-uniform on purpose: a per-sub-chunk flag -- bit 30 of sub_lo -- lets more threads take the plain
+                // variant but measured 23.3 us instead of 21.3: warps of one block then run different variants)
+                const bool rows_in = (fl & 2) != 0;
                 const float *lo0 = opaque(pv0 + c0), *lo1 = opaque(pv0 + c1);
-                const bool interior = has1 && c00 && c01 && c10 && c11;
-                const bool hot = (fl & 2) && __all_sync(__activemask(), interior);
+                // all taps of the warp's columns inside the detector (a vote: the variants compute the same values)?
+                const bool cols_in = __all_sync(__activemask(), has1 && c00 && c01 && c10 && c11);
                 float *o0 = opaque(ob + k0), *o1 = opaque(ob + k1);
                 const unsigned ofs = (unsigned)ii0 * plane;
-                if (hot) bp_march_rows<false>(ev_all[jr], s_lo, s_hi, lo0, lo1, o0, o1, ofs, plane, e2, w2, c00, c01, c10, c11, has1);
-                else bp_march_rows<true>(ev_all[jr], s_lo, s_hi, lo0, lo1, o0, o1, ofs, plane, e2, w2, c00, c01, c10, c11, has1);
+                if (cols_in && rows_in) bp_march_rows<false, false>(ev_all[jr], s_lo, s_hi, lo0, lo1, o0, o1, ofs, plane, e2, w2, c00, c01, c10, c11, has1);
+#ifndef LR_BP_NO_ROWCHK_VARIANT
+                else if (cols_in) bp_march_rows<true, false>(ev_all[jr], s_lo, s_hi, lo0, lo1, o0, o1, ofs, plane, e2, w2, c00, c01, c10, c11, has1);
+#endif
+                else bp_march_rows<true, true>(ev_all[jr], s_lo, s_hi, lo0, lo1, o0, o1, ofs, plane, e2, w2, c00, c01, c10, c11, has1);
             } else {
                 // generic geometry: per-plane table, per-tap predicates, same separable blend
                 float wq0, wq1, e0, e1;
@@ -557,12 +581,12 @@ template <bool CHK>
 __device__ __forceinline__ void bp_march_plan(const int2 *__restrict__ ev, int s_lo, int s_hi, const float *lo0, const float *lo1,
                                               float *o0, float *o1, unsigned plane, f32x2 e2, f32x2 w2, bool c00, bool c01,
                                               bool c10, bool c11, bool has1) {
-    f32x2 t_prev = bp_fetch_row<CHK>(lo0, lo1, __ldg(ev + s_lo).y, e2, w2, c00, c01, c10, c11);
+    f32x2 t_prev = bp_fetch_row<CHK, CHK>(lo0, lo1, __ldg(ev + s_lo).y, e2, w2, c00, c01, c10, c11);
     unsigned ofs = 0;
 #pragma unroll 4
     for (int s = s_lo + 1; s <= s_hi; ++s) {
         const int2 e = __ldg(ev + s);
-        const f32x2 t = bp_fetch_row<CHK>(lo0, lo1, e.y, e2, w2, c00, c01, c10, c11);
+        const f32x2 t = bp_fetch_row<CHK, CHK>(lo0, lo1, e.y, e2, w2, c00, c01, c10, c11);
         const float n = __int_as_float(e.x);
         if (n >= 0.0f) {
             const f32x2 n2 = splat2(n), s2 = splat2(sub_rn(1.0f, n));
@@ -713,6 +737,7 @@ static int fill_dims(BpDims &g, int B, int P, int pw, int ph, int d_total, int w
     g.proj_view_stride = (int64_t)pw * ph;
     g.out_batch_stride = obs; g.out_chan_stride = ocs;
     g.zero = 0.0f;
+    g.m_nj0 = g.m_nj1 = g.m_nj2 = g.m_chunks = g.m_views = 0;
     return LR_OK;
 }
 
@@ -779,6 +804,15 @@ static dim3 forward_shape(BpDims &g, int n_views, unsigned &grid, int min_thread
     rest -= g.nj1 * g.js1;
     g.nj2 = rest > 0 ? rest : 0;
     grid = (unsigned)((g.nj0 + g.nj1 + g.nj2) * g.n_vc);
+    auto magic = [&](int dvs) -> unsigned {      // exact for every block index of this grid, else 0 (plain division)
+#ifdef LR_BP_NO_MAGIC
+        return 0u;
+#endif
+        if (dvs <= 1 || (uint64_t)grid * (uint64_t)dvs >= (1ull << 32)) return 0u;
+        return (unsigned)(((1ull << 32) + (unsigned)dvs - 1) / (unsigned)dvs);
+    };
+    g.m_nj0 = magic(g.nj0); g.m_nj1 = magic(g.nj1); g.m_nj2 = magic(g.nj2);
+    g.m_chunks = magic(g.n_chunks); g.m_views = magic(g.n_views);
     return dim3((unsigned)g.bx, (unsigned)g.by, 1);
 }
 

@@ -9,19 +9,17 @@ namespace lr {
 // `iters` times with fully coalesced warp-wide 32-bit loads (one 128 B wavefront per LDG, 8 independent loads in
 // flight per thread): the ceiling of a kernel that gathers with scalar loads.  bytes = gridDim.x * 256 * iters * 32.
 __global__ void __launch_bounds__(256) probe_l1_gather_kernel(const float *__restrict__ buf, int floats_per_block, int iters,
-                                                              float *__restrict__ sink) {
-    // thread t reads floats t, t+256, ..., t+7*256 of the block's slice (2048 floats = 8 KB) over and over: the eight
-    // addresses differ by immediates, so the loop body is 8 LDG + 8 FADD + the loop counter
+                                                              int zero, float *__restrict__ sink) {
+    // thread t reads floats t, t+256, ..., t+7*256 of the block's slice (2048 floats = 8 KB) over and over.  `zero` is a
+    // run-time 0 folded into the address so that the loads cannot be hoisted out of the loop; the eight addresses differ
+    // by immediates, so the loop body is 8 LDG + 8 FADD + 2 integer instructions.
     const float *p = buf + (size_t)blockIdx.x * floats_per_block + threadIdx.x;
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 2
     for (int it = 0; it < iters; ++it) {
+        const float *q = p + (it & zero);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            float v;
-            asm volatile("ld.global.ca.f32 %0, [%1];" : "=f"(v) : "l"(p + u * 256));
-            acc[u] += v;
-        }
+        for (int u = 0; u < 8; ++u) acc[u] += __ldca(q + u * 256);
     }
     float s = 0.f;
 #pragma unroll
@@ -55,7 +53,7 @@ extern "C" int lr_probe_l1_gather(const float *buf, int64_t buf_floats, int bloc
     LR_REQUIRE(floats_per_block >= 2048 && (floats_per_block & (floats_per_block - 1)) == 0,
                "probe_l1_gather: floats_per_block must be a power of two >= 2048");
     LR_REQUIRE((int64_t)blocks * floats_per_block <= buf_floats, "probe_l1_gather: buffer too small");
-    probe_l1_gather_kernel<<<blocks, 256, 0, as_stream(stream)>>>(buf, floats_per_block, iters, sink);
+    probe_l1_gather_kernel<<<blocks, 256, 0, as_stream(stream)>>>(buf, floats_per_block, iters, 0, sink);
     return check_launch("probe_l1_gather_kernel");
 }
 

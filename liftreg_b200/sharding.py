@@ -2,10 +2,11 @@
 
 One process per GPU (`torch.distributed`, NCCL over NVLink/NVSwitch on the GPU box, gloo in the CPU tests):
 
-  * DRR forward      every ray is independent and needs the whole volume: the (batch x view) list is split across
-                     ranks, the volume is replicated, and the detector images are all-gathered (0.9 MB at cfg 1,
-                     67 MB at cfg 4: latency-bound).  Each rank's kernel writes straight into its slot of the
-                     gather buffer, so the collective is the only copy.
+  * DRR forward      every ray is independent and needs the whole volume: the (batch x view) list is dealt out to the
+                     ranks round-robin (neighbouring views cost the same, so interleaving balances the ranks), the
+                     volume is replicated, and the detector images are all-gathered (0.9 MB at cfg 1, 67 MB at cfg 4:
+                     latency-bound).  Each rank's kernel writes straight into its slot of the gather buffer
+                     (ops.drr_project(out=)), so the collective and the final de-interleave are the only copies.
   * backprojection   per-voxel gather from tiny, replicated projections: split the output along axis 0 (z-slabs);
                      no halo, no collective (the output stays sharded for the data-parallel consumer).
   * warp             split the OUTPUT along axis 0; phi is sharded like the output, the moving image is replicated
@@ -41,16 +42,23 @@ def _world(group):
 
 
 # --------------------------------------------------------------------------------------------- DRR: view sharding
+def interleaved_views(n_views, world, rank):
+    """Views of `rank` under the interleaved assignment rank, rank+world, ...: neighbouring views (similar obliqueness,
+    hence similar ray lengths and cost) go to different ranks, which balances the ranks better than contiguous blocks."""
+    return list(range(rank, n_views, world))
+
+
 def drr_project_sharded(vol, poses, resolution, spacing, y_norm_mode=0, out_scale=0.1, group=None, gather=True,
                         project_fn=None, buf=None):
     """View-sharded DRR.  vol (B,d,w,h) replicated on every rank; poses (P,3) or (B,P,3).
 
-    The flattened list of (b,p) views is split contiguously across ranks; each rank projects its views and, if
-    `gather`, the detector images are all-gathered so every rank returns the full (B,P,rd,rh).  With gather=False
-    the rank's own (n_local,rd,rh) images are returned together with its (start, stop) range.
+    The flattened list of (b,p) views is dealt out to the ranks round-robin (view v -> rank v % world); each rank
+    projects its views and, if `gather`, the detector images are all-gathered so every rank returns the full
+    (B,P,rd,rh).  With gather=False the rank's own (n_local,rd,rh) images are returned together with the list of its
+    view indices.
     `project_fn(vol_b (1,d,w,h), poses (n,3), resolution, spacing, y_norm_mode, out_scale) -> (1,n,rd,rh)` defaults
     to the CUDA op, which writes each rank's images directly into its slot of the gather buffer (`out=`), so the
-    collective is the only copy; the CPU tests inject the oracle (whose result is copied in).
+    collective is the only copy besides the final de-interleave; the CPU tests inject the oracle (whose result is copied in).
     `buf`: optional pre-allocated (world, slot, rd, rh) gather buffer (benchmarks reuse it across calls).
     """
     native = project_fn is None
@@ -65,33 +73,37 @@ def drr_project_sharded(vol, poses, resolution, spacing, y_norm_mode=0, out_scal
     P = p64.shape[1]
     rd, rh = int(resolution[0]), int(resolution[1])
     n_views = B * P
-    ranges = all_ranges(n_views, world)
-    v0, v1 = ranges[rank]
-    slot = max(hi - lo for lo, hi in ranges)              # all_gather needs equal-sized contributions
+    slot = (n_views + world - 1) // world                 # all_gather needs equal-sized contributions
     if buf is None:
         buf = torch.zeros((world, slot, rd, rh), device=vol.device, dtype=torch.float32)
     elif tuple(buf.shape) != (world, slot, rd, rh):
         raise ValueError("buf must be (%d,%d,%d,%d)" % (world, slot, rd, rh))
     mine = buf[rank]
-    v = v0
-    while v < v1:                                          # one call per batch item touched by [v0, v1)
-        b, p = divmod(v, P)
-        p_hi = min(P, p + (v1 - v))
-        slot_view = mine[v - v0:v - v0 + (p_hi - p)]       # the kernel writes straight into the gather buffer
+    my_views = interleaved_views(n_views, world, rank)
+    # one call per batch item: this rank's views of item b are p = p0, p0+world, ... (a strided slice of the poses)
+    i = 0
+    while i < len(my_views):
+        b = my_views[i] // P
+        k = i
+        while k < len(my_views) and my_views[k] // P == b:
+            k += 1
+        ps = np.ascontiguousarray(p64[b, [v - b * P for v in my_views[i:k]]])
+        slot_view = mine[i:k]                               # the kernel writes straight into the gather buffer
         if native:
-            project_fn(vol[b:b + 1], p64[b, p:p_hi], (rd, rh), spacing, y_norm_mode, out_scale, out=slot_view)
+            project_fn(vol[b:b + 1], ps, (rd, rh), spacing, y_norm_mode, out_scale, out=slot_view)
         else:
-            slot_view.copy_(project_fn(vol[b:b + 1], p64[b, p:p_hi], (rd, rh), spacing, y_norm_mode, out_scale)[0])
-        v += p_hi - p
+            slot_view.copy_(project_fn(vol[b:b + 1], ps, (rd, rh), spacing, y_norm_mode, out_scale)[0])
+        i = k
     if not gather:
-        return mine[:v1 - v0], (v0, v1)
+        return mine[:len(my_views)], my_views
     if world > 1:
         # NCCL gathers in place (the send slice already sits in the receive buffer); gloo wants a separate input
         send = mine.reshape(-1) if buf.is_cuda else mine.reshape(-1).clone()
         dist.all_gather_into_tensor(buf.view(-1), send, group=group)
-    if all(hi - lo == slot for lo, hi in ranges):         # equal shares: the gather buffer IS the result
+    if world == 1:
         return buf.view(B, P, rd, rh)
-    full = torch.cat([buf[r, :hi - lo] for r, (lo, hi) in enumerate(ranges)], dim=0)
+    # de-interleave: view v sits at buf[v % world, v // world]
+    full = buf.transpose(0, 1).reshape(world * slot, rd, rh)[:n_views]
     return full.reshape(B, P, rd, rh)
 
 

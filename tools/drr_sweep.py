@@ -54,7 +54,7 @@ def main():
             ms = float(t.item())
         if rank == 0:
             nominal = P * det[0] * det[1] * n
-            full = out if gather else out[0]
+            full = out if gather else out[0]          # (gather=False: this rank's images and its view list)
             print(json.dumps({"workload": "cfg4: DRR sweep 512^3, 64 views / 60 deg, 512^2 detector", "n_gpus": world,
                               "all_gather": gather, "ms_per_sweep": ms, "nominal_ray_samples": nominal,
                               "samples_per_s": nominal / ms * 1e3, "checksum": float(full.double().sum().item())}))
