@@ -297,7 +297,10 @@ __device__ __forceinline__ void warp_pair_fast(const float *__restrict__ src, fl
     floor2_fi(iy, fy, y0a, y0b);
     floor2_fi(iz, fz, z0a, z0b);
     // packed path: both y/z tap pairs inside and at least one x tap inside (as warp_pair); NaN / far-out coordinates
-    // floor to indices outside any volume and take the scalar path
+    // floor to indices outside any volume and take the scalar path.  (Masking the y / z faces here as well, so that the
+    // ~8 % of voxel pairs on the faces and the displaced rim stay on the packed path, was measured slower: forward 20.8
+    // vs 20.5 us, d/dphi 33.5 vs 31.9 us -- the twelve extra predicates cost the interior pairs more than the scalar path
+    // costs the rim.)
     const bool ina = (unsigned)(x0a + 1) < (unsigned)(g.W + 1) && (unsigned)y0a < (unsigned)(g.H - 1) && (unsigned)z0a < (unsigned)(g.D - 1);
     const bool inb = (unsigned)(x0b + 1) < (unsigned)(g.W + 1) && (unsigned)y0b < (unsigned)(g.H - 1) && (unsigned)z0b < (unsigned)(g.D - 1);
     if (ina && inb) {
@@ -728,7 +731,7 @@ static dim3 warp_grid(int nb, int D, int H, int W, int rows_per_thread = 1) {
 // (~15 % of the kernel at 160^3).  So the blocks taper: most planes go into 8-plane blocks (set-up amortised), the rest
 // into 4- and 2-plane blocks that are dispatched last (per batch item) and fill the tail.  The short blocks' share is about 1.2 waves of
 // work, at most 45 % (measured: 55/27/18 % is best at batch 1 = 1.7 waves, 100/0/0 at batch 8 = 13.5 waves).
-static void forward_z_blocking(WarpDims &g, int n_batch) {
+static void forward_z_blocking(WarpDims &g, int n_batch, double resident_blocks = 4.0, double max_small = 0.45) {
     static int f0_env = -1, f1_env = -1;        // LIFTREG_B200_WARP_TAPER="f0,f1": percent of the planes in 8- / 4-plane blocks
     if (f0_env == -1) {
         int a = -2, b = -2;     // kernel experiments; anything that does not parse as two sane percentages is ignored
@@ -746,9 +749,9 @@ static void forward_z_blocking(WarpDims &g, int n_batch) {
         int f0 = f0_env, f1 = f1_env;
         if (f0 < 0) {
             const double tiles = (double)((g.W + WARP_TX - 1) / WARP_TX) * ((g.H + WARP_TY * WARP_VY - 1) / (WARP_TY * WARP_VY));
-            const double waves = tiles * n_batch * ((Do + g.zs0 - 1) / g.zs0) / (4.0 * sm_count());   // tuned with this count
+            const double waves = tiles * n_batch * ((Do + g.zs0 - 1) / g.zs0) / (resident_blocks * sm_count());   // (tuned with these counts)
             double small = 1.2 / (waves > 0.1 ? waves : 0.1);
-            if (small > 0.45) small = 0.45;
+            if (small > max_small) small = max_small;
             f0 = (int)(100.0 * (1.0 - small) + 0.5);
             f1 = (int)(100.0 * 0.6 * small + 0.5);
         }
@@ -883,7 +886,7 @@ extern "C" int lr_warp_backward_slab(const float *grad_out, const float *img, co
         if (padding == LR_PAD_ZEROS && !gi) {
             // training configuration: map gradient only -> packed two-voxel kernel
             WarpDims gz = g;                      // this kernel walks runs of planes (tapered z-blocks, as the forward)
-            forward_z_blocking(gz, nb);
+            forward_z_blocking(gz, nb, 6.0, 0.5);  // 6 resident blocks per SM; measured at 160^3: 50/30/20 % -> 32.0 us, 64/21/15 % -> 33.2 us
             const dim3 grid2 = warp_grid(nb, gz.zblocks, H, W, WARP_VY);
             const dim3 blk(WARP_TX, WARP_TY);
 #define LR_LAUNCH_BWD_PHI(S, I)                                                                                              \

@@ -431,6 +431,69 @@ def test_host_entry_points_match_device_entry_points(dev, numerics):
     assert_ref(vol, gb["out"], numerics)
 
 
+def test_async_host_entry_points_overlap_and_match(dev, numerics):
+    """lr_*_host_async on two streams + lr_stream_synchronize (the overlapped e2e path of bench.py) against the blocking
+    calls: same bits; the async calls return before their results are complete only if the caller does not sync."""
+    import ctypes
+    from liftreg_b200 import _native, ops
+    lib = _native.lib()
+    g, gb = load_golden("warp_small"), load_golden("backproj_small")
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    img, phi = pin(g["img"]), pin(g["phi"])
+    B, C, D, H, W = img.shape
+    tp, poses = pin(gb["target_proj"]), np.ascontiguousarray(gb["poses"][0])
+    Bp, P, pw, ph = tp.shape
+    d, w, h = (int(s) for s in gb["img_shape"])
+    out_w, out_b = torch.zeros(img.shape).pin_memory(), torch.zeros((Bp, P, d, w, h)).pin_memory()
+    ws_w = torch.empty(lib.lr_warp_forward_host_workspace_bytes(B, C, D, H, W), dtype=torch.uint8, device=dev)
+    ws_b = torch.empty(lib.lr_backproject_forward_host_workspace_bytes(Bp, P, pw, ph, d, w, h), dtype=torch.uint8, device=dev)
+    sa, sb = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())
+    _native.check(lib.lr_backproject_forward_host_async(vp(tp), ops._fp(poses), Bp, P, pw, ph, d, w, h, vp(out_b), vp(ws_b), ws_b.numel(),
+                                                        ctypes.c_void_p(sa.cuda_stream)), "bp async")
+    _native.check(lib.lr_warp_forward_host_async(vp(img), vp(phi), B, C, D, H, W, 0, 0, 1, 0, vp(out_w), vp(ws_w), ws_w.numel(),
+                                                 ctypes.c_void_p(sb.cuda_stream)), "warp async")
+    _native.check(lib.lr_stream_synchronize(ctypes.c_void_p(sa.cuda_stream)), "sync a")
+    _native.check(lib.lr_stream_synchronize(ctypes.c_void_p(sb.cuda_stream)), "sync b")
+    assert_ref(out_w.numpy(), g["out_zb1_us1_bilinear"], numerics)
+    assert_ref(out_b.numpy(), gb["out"], numerics)
+    ref_w, ref_b = np.empty_like(g["img"]), np.empty((Bp, P, d, w, h), np.float32)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _native.check(lib.lr_warp_forward_host(g["img"].ctypes.data, g["phi"].ctypes.data, B, C, D, H, W, 0, 0, 1, 0, ref_w.ctypes.data,
+                                           vp(ws_w), ws_w.numel(), st), "warp host")
+    _native.check(lib.lr_backproject_forward_host(gb["target_proj"].ctypes.data, ops._fp(poses), Bp, P, pw, ph, d, w, h, ref_b.ctypes.data,
+                                                  vp(ws_b), ws_b.numel(), st), "bp host")
+    assert np.array_equal(out_w.numpy(), ref_w) and np.array_equal(out_b.numpy(), ref_b)
+
+
+def test_probe_kernels_report_plausible_peaks(dev):
+    """bench.py's DRR fractions divide by these: L1-hit gather bandwidth between 5 and 40 TB/s (148 SMs x 128 B/clk x
+    1.965 GHz = 37 TB/s), issue rate between 0.5 and 1.2 T warp-instructions/s (592 schedulers x 1.965 GHz = 1.16 T)."""
+    import ctypes
+    from liftreg_b200 import _native
+    lib = _native.lib()
+    sm = torch.cuda.get_device_properties(dev).multi_processor_count
+    blocks, fpb, iters = sm * 8, 4096, 500
+    buf, sink = torch.zeros(blocks * fpb, device=dev), torch.zeros(4, device=dev)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())
+
+    def ms(fn):
+        fn(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 3
+
+    t = ms(lambda: _native.check(lib.lr_probe_l1_gather(vp(buf), buf.numel(), blocks, fpb, iters, vp(sink), st), "probe"))
+    assert 5e3 <= blocks * 256 * iters * 32 / t * 1e-6 <= 40e3
+    t = ms(lambda: _native.check(lib.lr_probe_issue(blocks, 1000, vp(sink), st), "probe"))
+    assert 500 <= blocks * 8 * 1000 * 8 / t * 1e-6 <= 1200
+    assert lib.lr_probe_l1_gather(vp(buf), buf.numel(), blocks, 1000, iters, vp(sink), st) == -1          # not a power of two
+
+
 # ------------------------------------------------------------------ error behaviour
 def test_bad_arguments_are_reported_not_crashed(dev):
     import ctypes

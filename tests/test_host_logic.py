@@ -201,3 +201,27 @@ def test_backproject_forward_plan_tiles_planes_and_rows_once(B):
                     j += run
             assert (rows == 1).all(), (d, w, h, P, B)
             assert grid == (n0 + n1 + n2) * n_chunks * min(P, 64) * B
+
+
+def test_numerics_mode_is_settable_without_a_gpu_and_rejects_bad_values():
+    """lr_set_numerics / lr_get_numerics (include/liftreg_b200.h): process-wide, no device work."""
+    from liftreg_b200 import _native
+    lib = _native.lib()
+    prev = _native.get_numerics()
+    try:
+        assert _native.set_numerics("exact") == prev and _native.get_numerics() == "exact" and lib.lr_get_numerics() == 1
+        assert _native.set_numerics("fast") == "exact" and lib.lr_get_numerics() == 0
+        assert lib.lr_set_numerics(7) == -1 and b"mode" in lib.lr_last_error()
+        assert lib.lr_get_numerics() == 0
+    finally:
+        _native.set_numerics(prev)
+
+
+def test_backproject_plan_size_and_argument_checks_without_a_gpu():
+    from liftreg_b200 import _native
+    lib = _native.lib()
+    n = lib.lr_backproject_plan_bytes(4, 256, 256, 160, 160, 160)
+    # one record per (view, row): header + rowtab[d] + evtab[3d+8] + coltab[h], 8 bytes per entry, 16-byte aligned
+    rec_words = (4 + 2 * 160 + 2 * (3 * 160 + 8) + 2 * 160 + 3) // 4 * 4
+    assert n == 4 * 160 * rec_words * 4
+    assert lib.lr_backproject_plan_bytes(0, 256, 256, 160, 160, 160) == 0
