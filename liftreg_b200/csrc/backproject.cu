@@ -66,11 +66,12 @@ struct AxisTap {      // one axis of the bilinear footprint
 };
 
 // normalised coordinate -> (floor index, upper weight), ATen vector-kernel order
-__device__ __forceinline__ AxisTap axis_tap(float centred, float s_c, float scale, ConstDiv size, float half_sm1) {
+__device__ __forceinline__ AxisTap axis_tap(float centred, float s_c, float scale, ConstDiv size, float half_sm1, float wide = 0.0f) {
     float a = add_rn(mul_rn(sub_rn(centred, s_c), scale), s_c);   // (x - s)*scale + s
     float g = mul_rn(div_const(a, size), 2.0f);                   // / size * 2
     float ix = mul_rn(add_rn(g, 1.0f), half_sm1);                 // (g+1)*((S-1)/2)
-    ix = clamp_index(ix, half_sm1 * 2.0f + 3.0f);                 // beyond [-2, S+1] no tap is in bounds
+    // beyond [-2, S+1] no tap is in bounds; `wide` (the plan builder) only keeps floor_fi's |x| < 2^22 precondition
+    ix = wide > 0.0f ? fminf(fmaxf(ix, -wide), wide) : clamp_index(ix, half_sm1 * 2.0f + 3.0f);
     float fl;
     AxisTap t;
     floor_fi(ix, fl, t.i0);
@@ -502,8 +503,12 @@ __global__ void LR_BP_ROWS_BOUNDS
 // into a caller-owned device buffer (3 MB at cfg 2, L2-resident) and backproject_forward_plan_kernel only marches:
 // no shared memory, no barrier, no division, no axis_tap chain in the hot kernel.  MEASURED (profiles/README.md, round 2):
 // 30.4 us against 23.4 us for the rows kernel at cfg 2 -- the per-row table entry becomes a dependent global load (L2
-// latency) at the head of every gather, which costs more than rebuilding the tables in shared memory.  The entry
-// points are kept (any z-slab / stride, bit-identical results, tested) but ops.backproject does not use them.
+// latency) at the head of every gather, which costs more than rebuilding the tables in shared memory.  (After the
+// builder stopped clamping far-outside rows -- which had sent 31 % of the rows down the generic path -- it is 25.3 us;
+// a variant that first stages the block's slice of the plan in shared memory and then runs the rows kernel's march:
+// 27.6 us, 22 us per item at batch 8 against 17: every block starts with two L2 round trips during which its warps
+// idle, whereas the rows kernel's table building is arithmetic on kernel parameters.)  The entry points are kept (any
+// z-slab / stride, bit-identical results, tested) but ops.backproject does not use them.
 // One record per (view p, coronal row j), 16-byte aligned, all 4-byte words:
 //   [0] r_base   floor detector row of plane 0      [1] flags  bit 0: planes move strictly down the detector and the
 //   [2] n_slots  rows r_base .. r_base+n_slots-1         row range fits the event table (fast path allowed)
@@ -535,7 +540,10 @@ __global__ void __launch_bounds__(256) backproject_plan_kernel(int *__restrict__
     int2 *evtab = reinterpret_cast<int2 *>(rec + L.evtab());
     int2 *coltab = reinterpret_cast<int2 *>(rec + L.coltab());
     for (int i = threadIdx.x; i < L.d; i += blockDim.x) {
-        const AxisTap t = axis_tap((float)i - g.half_d, sx, scale, g.div_pw, g.hpw);
+        // wide clamp: planes whose detector rows lie far outside keep DISTINCT floor rows (axis_tap's clamp to [-2, S+2]
+        // would make them equal and fail the strictly-increasing test for the whole row j; their taps are skipped either
+        // way, so the result is the same)
+        const AxisTap t = axis_tap((float)i - g.half_d, sx, scale, g.div_pw, g.hpw, 2097152.0f);
         rowtab[i] = make_int2(t.i0, __float_as_int(t.w1));
     }
     for (int k = threadIdx.x; k < L.h; k += blockDim.x) {
