@@ -265,6 +265,22 @@ LR_API int lr_ncc_sums(const float *x, const float *y, int B, int64_t N, double 
 LR_API int lr_ncc_backward(const float *x, const float *y, int B, int64_t N, const double *sums, const float *grad_loss,
                            float *grad_x, lr_stream_t stream);
 
+/* ---- displacement regulariser of the subspace loss ---- */
+/* replaces src/liftreg/losses/SubspaceLoss.py:51-67 compute_reg_loss (same code: losses/RegNet2D3DLoss.py:53-69):
+ *   fd = mermaid.finite_differences.FD_torch(spacing*2), spacing = 1/(shape-1);
+ *   reg = mean over (B, D, H, W) of sum_{c<3} dXc(disp_c)^2 + dYc(disp_c)^2 + dZc(disp_c)^2
+ * disp (B,3,D,H,W) float32, dense.  mermaid (third party, requirements.txt:61) is not part of the reference tree; its
+ * central difference is (I[i+1]-I[i-1]) * 0.5/spacing in the interior, and on the faces either a linear extrapolation
+ * of the missing neighbour (LR_FD_LINEAR, FD_torch's default mode) or zero (LR_FD_NEUMANN_ZERO).
+ * lr_diffusion_reg_sum: *sum (one float64 in device memory, zeroed by the call) = sum over every voxel of the nine
+ *   squares; reg = *sum / (B*D*H*W).
+ * lr_diffusion_reg_backward: grad_disp (B,3,D,H,W) = d(reg)/d(disp) * grad_loss[0] (one float in device memory). */
+#define LR_FD_LINEAR 0
+#define LR_FD_NEUMANN_ZERO 1
+LR_API int lr_diffusion_reg_sum(const float *disp, int B, int D, int H, int W, int boundary, double *sum, lr_stream_t stream);
+LR_API int lr_diffusion_reg_backward(const float *disp, int B, int D, int H, int W, int boundary, const float *grad_loss,
+                                     float *grad_disp, lr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

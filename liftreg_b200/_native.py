@@ -55,6 +55,8 @@ SIGNATURES = {
     "lr_probe_issue": (_i, [_i, _i, _vp, _vp]),
     "lr_ncc_sums": (_i, [_vp, _vp, _i, _i64, _vp, _vp]),
     "lr_ncc_backward": (_i, [_vp, _vp, _i, _i64, _vp, _vp, _vp, _vp]),
+    "lr_diffusion_reg_sum": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "lr_diffusion_reg_backward": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -867,6 +867,54 @@ def test_ncc_loss_vs_torch_port(dev, B, shape):
     assert rel_l2(x.grad.cpu().numpy(), xr.grad.numpy()) <= GRAD_TOL
 
 
+@pytest.mark.parametrize("boundary", ["linear", "neumann_zero"])
+@pytest.mark.parametrize("B,shape", [(1, (160, 160, 160)), (2, (17, 33, 40)), (3, (5, 6, 7)), (1, (2, 2, 2)), (1, (3, 2, 70)),
+                                     (2, (6, 5, 33)), (1, (4, 4, 4)), (2, (7, 9, 6)), (1, (35, 3, 2))])
+def test_diffusion_regulariser_vs_torch_port(dev, B, shape, boundary):
+    """SubspaceLoss.py:51-67 (mermaid central differences, both face rules): the fused kernel's value against the fp32
+    torch restatement and its float64 evaluation, the gradient against autograd through the float64 one.  Even row
+    lengths run the two-voxels-per-thread kernels, odd ones the scalar kernels."""
+    from liftreg_b200 import ops
+    from oracle import torch_port
+    rs = np.random.RandomState(71)
+    disp = (0.05 * rs.standard_normal((B, 3) + shape)).astype(np.float32)
+    x = cu(disp, dev).requires_grad_(True)
+    reg = ops.diffusion_reg(x, boundary)
+    (0.7 * reg).backward()
+    xr = torch.from_numpy(disp).double().requires_grad_(True)
+    ref = torch_port.diffusion_reg(xr, boundary)
+    (0.7 * ref).backward()
+    ref32 = torch_port.diffusion_reg(torch.from_numpy(disp), boundary).item()
+    assert abs(reg.item() - ref.item()) <= 2e-6 * abs(ref.item())
+    assert abs(reg.item() - ref32) <= 1e-5 * abs(ref32)            # torch.mean's fp32 cascade vs fp64 accumulation here
+    assert rel_l2(x.grad.cpu().numpy(), xr.grad.numpy()) <= GRAD_TOL
+
+
+def test_subspace_loss_mirror(dev):
+    """losses.SubspaceLoss == sim_factor * NCC + reg_factor(epoch) * regulariser (SubspaceLoss.py:20-37), through autograd."""
+    from liftreg_b200 import losses
+    from oracle import torch_port
+    rs = np.random.RandomState(72)
+    shape = (12, 14, 10)
+    target = rs.uniform(-1, 1, (2, 1) + shape).astype(np.float32)
+    warped = (0.5 * target + 0.5 * rs.uniform(-1, 1, (2, 1) + shape)).astype(np.float32)
+    params = (0.05 * rs.standard_normal((2, 3) + shape)).astype(np.float32)
+    crit = losses.loss({"initial_reg_factor": 10, "min_reg_factor": 1e-3, "reg_factor_decay_from": 10})
+    w, p = cu(warped, dev).requires_grad_(True), cu(params, dev).requires_grad_(True)
+    for epoch in (0, 14):
+        out = crit({"warped": w, "target": cu(target, dev), "params": p, "pca_coefs": None, "epoch": epoch})
+        wr, pr = torch.from_numpy(warped).double().requires_grad_(True), torch.from_numpy(params).double().requires_grad_(True)
+        factor = max(losses.sigmoid_decay(epoch, static=10, k=2) * 10, 1e-3)
+        ref = torch_port.ncc_loss(wr, torch.from_numpy(target).double()) + factor * torch_port.diffusion_reg(pr)
+        assert abs(out["total_loss"].item() - ref.item()) <= 1e-5 * abs(ref.item())
+        assert abs(out["sim_loss"] + crit.get_reg_factor(epoch) * out["reg_loss"] - out["total_loss"].item()) <= 1e-5
+        w.grad = p.grad = None
+        out["total_loss"].backward()
+        ref.backward()
+        assert rel_l2(w.grad.cpu().numpy(), wr.grad.numpy()) <= GRAD_TOL
+        assert rel_l2(p.grad.cpu().numpy(), pr.grad.numpy()) <= GRAD_TOL
+
+
 def test_label_warp_mirror_of_mermaid_entry_point(dev):
     """RegistrationNet.py:191-196: compute_warped_image_multiNC(labels, phi, spacing, spline_order=0, zero_boundary=True,
     use_01_input=False) == nearest-mode spatial transformer without intensity rescaling (pinned nearest arithmetic)."""
