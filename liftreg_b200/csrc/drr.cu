@@ -386,6 +386,98 @@ __global__ void __launch_bounds__(32 * DRR_ROWS)
     }
 }
 
+// Warp-aggregated adjoint.  The scatter above is bound by the number of atomics reaching L2 (measured: half the atomics
+// = half the time, profiles/README.md), and the 32 rays of a warp -- neighbours along detector axis 1, marching the same
+// plane j -- hit heavily overlapping cells: consecutive lanes share their floor cell or sit one cell further along the
+// volume's contiguous axis, so lane l's upper-x tap is lane l+1's lower-x tap.  Per plane the warp therefore
+//   1. sums the 8 tap values of runs of consecutive lanes with the same floor cell into the run's first lane,
+//   2. hands a run's four upper-x sums to the next run when that run's cell is the next one along x,
+// and only then issues the atomics: ~22 cells x 4 rows instead of 32 x 8 per plane at cfg 1 (2.8x fewer).  Both steps are
+// exact regroupings of the same sum (fp32 addition order differs, as it already does between runs of the scatter).
+__global__ void __launch_bounds__(32 * DRR_ROWS)
+    drr_backward_agg_kernel(const float *__restrict__ gproj, float *__restrict__ gvol, DrrDims g, DrrViews views) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x;
+    const int v = blockIdx.x * 32 + lane;
+    const int u = blockIdx.y * DRR_ROWS + threadIdx.y;
+    if (u >= g.rd) return;                                   // whole warp (u is warp-uniform)
+    const DrrView vw = views.v[blockIdx.z];
+    const bool live_ray = v < g.rh;
+    const Ray r = ray_setup(vw, g, u, live_ray ? v : g.rh - 1);
+    float *V = gvol + (int64_t)vw.vol * g.nvox;
+    const int sy = g.h, sz = g.w * g.h;
+    float go = live_ray ? gproj[((int64_t)(g.view0 + blockIdx.z) * g.rd + u) * g.rh + v] : 0.0f;
+    if (g.out_scale != 1.0f) go = mul_rn(go, g.out_scale);
+    const float gs = mul_rn(go, r.dx);
+    const bool ray_on = live_ray && gs != 0.0f && r.j0 <= r.j1;
+    const int jlo = __reduce_min_sync(FULL, ray_on ? r.j0 : 0x7fffffff);
+    const int jhi = __reduce_max_sync(FULL, ray_on ? r.j1 : (int)0x80000000);
+    float jf = (float)jlo;
+    for (int j = jlo; j <= jhi; ++j, jf += 1.0f) {
+        float val[8];
+        unsigned m = 0u;
+        int key = (int)0x80000000 + 2 * lane;                // dead lanes: unique, never equal or adjacent to a cell
+        if (ray_on && j >= r.j0 && j <= r.j1) {
+            const Sample s = ray_point(r, g, jf);
+            const Taps t = make_taps(s, g);
+            m = taps_mask(t, g);
+            if (m != 0u) key = t.base;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) val[c] = ((m >> c) & 1u) ? mul_rn(t.wt[c], gs) : 0.0f;
+        } else {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) val[c] = 0.0f;
+        }
+        if (__ballot_sync(FULL, m != 0u) == 0u) continue;     // no lane touches the volume on this plane
+        // ---- runs of consecutive lanes with the same floor cell
+        const int key_prev = __shfl_up_sync(FULL, key, 1);
+#ifndef LR_DRR_AGG_MERGE
+#define LR_DRR_AGG_MERGE 1
+#endif
+        const bool follows = LR_DRR_AGG_MERGE && lane > 0 && m != 0u && key == key_prev;
+        const unsigned long long E = (unsigned long long)__ballot_sync(FULL, follows);
+        const bool leader = m != 0u && !follows;
+        const int len = leader ? __ffsll((long long)~(E >> (lane + 1))) : 0;      // 1 + set bits of E right above this lane
+        const int K = LR_DRR_AGG_MERGE ? (int)__reduce_max_sync(FULL, (unsigned)(len > 0 ? len - 1 : 0)) : 0;
+        for (int k = 1; k <= K; ++k) {
+            const bool take = leader && k < len;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float o = __shfl_down_sync(FULL, val[c], k);
+                if (take) val[c] = add_rn(val[c], o);
+            }
+            const unsigned om = __shfl_down_sync(FULL, m, k);
+            if (take) m |= om;
+        }
+        // ---- upper-x taps (odd c) of a run go to the next run when its cell is the next one along x
+        const unsigned L = __ballot_sync(FULL, leader);
+        const int nl = lane + len;                                               // first lane after this run
+        const int key_next = __shfl_sync(FULL, key, nl & 31);
+        const bool give = leader && nl < 32 && key_next == key + 1;
+        const unsigned below = L & ((1u << lane) - 1u);
+        const int p = below ? 31 - __clz((int)below) : 0;                        // leader of the previous run
+        const int key_p = __shfl_sync(FULL, key, p);
+        const int len_p = __shfl_sync(FULL, len, p);
+        const unsigned m_p = __shfl_sync(FULL, m, p);
+        const bool recv = leader && below != 0u && p + len_p == lane && key_p + 1 == key;
+#pragma unroll
+        for (int rrow = 0; rrow < 4; ++rrow) {
+            const float o = __shfl_sync(FULL, val[2 * rrow + 1], p);
+            if (recv) val[2 * rrow] = add_rn(val[2 * rrow], o);
+        }
+        if (recv) m |= (m_p >> 1) & 0x55u;
+        if (give) m &= 0x55u;
+        if (leader) {
+            float *b = V + key;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int off = (c & 1) + ((c >> 1) & 1) * sy + (c >> 2) * sz;
+                if ((m >> c) & 1u) red_add(b + off, val[c]);
+            }
+        }
+    }
+}
+
 // sdct:15-57 materialised, for API parity / bit-exactness checks only.
 __global__ void __launch_bounds__(32 * DRR_ROWS)
     project_grid_kernel(float *__restrict__ grid, float *__restrict__ dx, DrrDims g, DrrViews views, int flip) {
@@ -479,6 +571,12 @@ extern "C" int lr_drr_backward(const float *grad_proj, int B, int d, int w, int 
     return for_each_view_chunk(poses, n_pose_sets, B, P, [&](int n, const DrrViews &vs, int v0) {
         g.view0 = v0;
         dim3 grid((unsigned)((rh + 31) / 32), (unsigned)((rd + DRR_ROWS - 1) / DRR_ROWS), (unsigned)n);
+        // LIFTREG_B200_DRR_BWD_AGG=0 selects the plain per-sample scatter
+        static const bool agg = [] { const char *e = getenv("LIFTREG_B200_DRR_BWD_AGG"); return !(e && e[0] == '0'); }();
+        if (agg) {
+            drr_backward_agg_kernel<<<grid, dim3(32, DRR_ROWS), 0, as_stream(stream)>>>(grad_proj, grad_vol, g, vs);
+            return check_launch("drr_backward_agg_kernel");
+        }
         drr_backward_kernel<<<grid, dim3(32, DRR_ROWS), 0, as_stream(stream)>>>(grad_proj, grad_vol, g, vs);
         return check_launch("drr_backward_kernel");
     });
