@@ -227,6 +227,31 @@ def test_drr_backward_vs_oracle_and_adjoint_identity(dev):
     assert abs(lhs - rhs) <= 1e-5 * abs(lhs)
 
 
+@pytest.mark.parametrize("shape,res,P", [((10, 12, 9), (37, 70), 2),        # 8 rays per voxel: long runs of equal cells
+                                         ((20, 16, 40), (33, 45), 3),       # ~1 ray per voxel: adjacent cells
+                                         ((9, 8, 50), (12, 20), 2),         # rays 2.5 voxels apart: nothing to merge
+                                         ((6, 5, 4), (3, 1), 1)])           # one lane alive per warp
+def test_drr_backward_warp_aggregation_vs_oracle(dev, shape, res, P):
+    """The warp-aggregated adjoint (runs of equal cells summed, upper-x taps handed to the neighbouring run) against the
+    oracle's per-sample scatter, with zero gradients sprinkled in (rays that drop out of the merge) and detector widths
+    that leave dead lanes in the last warp."""
+    from liftreg_b200 import ops, synthetic
+    from oracle import c_oracle
+    rs = np.random.RandomState(11)
+    go = rs.randn(2, P, *res).astype(np.float32)
+    go[rs.rand(*go.shape) < 0.2] = 0.0
+    poses = synthetic.wrapper_poses(60.0, P, shape[1])
+    v = torch.zeros((2,) + shape, device=dev, requires_grad=True)
+    y = ops.drr_project(v, poses, res, (2.2, 2.2, 2.2))
+    y.backward(cu(go, dev))
+    ora = c_oracle.drr_backward(go, shape, poses, (2.2, 2.2, 2.2))
+    assert rel_l2(v.grad.cpu().numpy(), ora) <= GRAD_TOL
+    w = cu(rs.rand(2, *shape).astype(np.float32), dev)                     # <DRR(w), g> == <w, DRR^T(g)>
+    lhs = float((ops.drr_project(w, poses, res, (2.2, 2.2, 2.2)).double() * cu(go, dev).double()).sum())
+    rhs = float((w.double() * v.grad.double()).sum())
+    assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), 1e-3)
+
+
 # ------------------------------------------------------------------ backprojection
 def test_backproj_grid_bit_exact_vs_reference_golden(dev):
     from liftreg_b200 import sdct_projection_utils as sdct
