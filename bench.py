@@ -433,9 +433,25 @@ def section_cfg4(b):
     slot = (Pn + b.world - 1) // b.world
     buf = torch.zeros((b.world, slot) + det, device=dev)           # gather buffer, reused by every sweep
     reps = 3 if b.world == 1 else 10
-    ms = event_time_ms(b, lambda: sharding.drr_project_sharded(tv, poses, det, sp, buf=buf), reps, warm=1)
+    ms_nccl = event_time_ms(b, lambda: sharding.drr_project_sharded(tv, poses, det, sp, buf=buf), reps, warm=1)
     ms_nogather = event_time_ms(b, lambda: sharding.drr_project_sharded(tv, poses, det, sp, buf=buf, gather=False), reps, warm=1)
     full = sharding.drr_project_sharded(tv, poses, det, sp, buf=buf)
+    # exchange form (a): the DRR kernel stores into every rank's gather buffer over NVLink (CUDA IPC peer memory); only a
+    # 4-byte all-reduce remains as barrier.  Falls back to the NCCL all-gather above if the peer mapping cannot be set up.
+    pg, peer_err, ms_peer, ok_peer = None, None, None, True
+    if b.world > 1:
+        try:
+            pg = sharding.PeerGather(Pn, det[0], det[1], dev)
+        except Exception as e:                                   # noqa: BLE001  (reported in the JSON line)
+            peer_err = "%s: %s" % (type(e).__name__, e)
+        if not b.all_true(pg is not None):
+            if pg is not None:
+                pg.close()
+            pg = None
+    if pg is not None:
+        ms_peer = event_time_ms(b, lambda: sharding.drr_project_sharded(tv, poses, det, sp, peers=pg), reps, warm=2)
+        ok_peer = bool(torch.equal(sharding.drr_project_sharded(tv, poses, det, sp, peers=pg), full))
+    ms = ms_peer if ms_peer is not None else ms_nccl
     # parity in the run: every rank recomputes a strided subset of the views unsharded and compares bit for bit; rank 0
     # compares ALL views (and so also times the 1-GPU sweep)
     sub = list(range((b.rank * 5) % Pn, Pn, max(1, b.world) + 3))[:4]        # views computed by OTHER ranks too
@@ -450,13 +466,18 @@ def section_cfg4(b):
         ms_one = e0.elapsed_time(e1)
         ok = ok and bool(torch.equal(full, ref))
         del ref
-    ok = b.all_true(ok)
+    ok = b.all_true(ok and ok_peer)
+    if pg is not None:
+        pg.close()
     nominal = Pn * det[0] * det[1] * n
     gather_bytes = 4 * Pn * det[0] * det[1]
     out = {"workload": "cfg4: DRR sweep 512^3, 64 views / 60 deg, 512^2 detector; views dealt round-robin to %d rank(s), volume "
-                       "replicated, NCCL all-gather of the images (+ de-interleave) inside the timed window" % b.world,
+                       "replicated, exchange of the images (see `exchange`) inside the timed window" % b.world,
            "scaling": "strong", "ms_per_sweep": ms, "ms_per_sweep_without_all_gather": ms_nogather,
-           "all_gather_ms": max(0.0, ms - ms_nogather), "all_gather_bytes": gather_bytes,
+           "exchange": ("p2p stores from the DRR kernel into every rank's buffer (CUDA IPC over NVLink) + 4-byte all-reduce"
+                        if ms_peer is not None else "NCCL all-gather + de-interleave" + (" (peer setup failed: %s)" % peer_err if peer_err else "")),
+           "ms_per_sweep_p2p_stores": ms_peer, "ms_per_sweep_nccl_all_gather": ms_nccl,
+           "all_gather_ms": max(0.0, ms_nccl - ms_nogather), "all_gather_bytes": gather_bytes,
            "nominal_ray_samples": nominal, "samples_per_s": nominal / ms * 1e3, "views_per_rank": slot,
            "one_gpu_unsharded_ms_on_rank0": ms_one, "sharded_parity": ok,
            "limiter": "the DRR kernel itself (issue/latency-bound, see drr_forward_cfg1); beyond it the all-gather "

@@ -95,6 +95,28 @@ LR_API int lr_drr_forward(const float *vol, int B, int d, int w, int h,
                           const float spacing[3], int y_norm_mode, float out_scale,
                           float *proj, lr_stream_t stream);
 
+/* Multi-GPU form of lr_drr_forward for view-sharded sweeps (BASELINE.json north star: "forward projection by view angle
+ * ..., all-gather of the detector images over NVLink"; the reference itself is single-GPU, main.py:108-110).  The kernel
+ * stores every detector pixel into n_outs buffers -- this rank's gather buffer and the peers' (device pointers obtained
+ * with lr_peer_open, written as P2P stores over NVLink) -- so the images need no collective afterwards, only a barrier.
+ * View k of the call (k = b*P + p) lands at outs[i] + k * view_stride * rd * rh: with view_stride = world size and
+ * outs[i] pointing at this rank's first view, a rank that owns the views r, r+world, ... fills the full (n_views,rd,rh)
+ * array in view order on every rank. */
+#define LR_MAX_PEERS 8
+LR_API int lr_drr_forward_peers(const float *vol, int B, int d, int w, int h,
+                                const double *poses, int n_pose_sets, int P, int rd, int rh,
+                                const float spacing[3], int y_norm_mode, float out_scale,
+                                float *const *outs, int n_outs, int view_stride, lr_stream_t stream);
+/* Peer-visible device buffers for the call above (CUDA IPC, one process per GPU on one box).
+ * lr_peer_alloc: cudaMalloc on the current device + its 64-byte IPC handle (to be sent to the other ranks by any means).
+ * lr_peer_open: maps another rank's buffer into this process (peer access enabled lazily); lr_peer_close unmaps it.
+ * lr_peer_free releases a buffer obtained from lr_peer_alloc (after the peers closed it). */
+#define LR_IPC_HANDLE_BYTES 64
+LR_API int lr_peer_alloc(size_t bytes, void **dev_ptr, unsigned char handle[LR_IPC_HANDLE_BYTES]);
+LR_API int lr_peer_open(const unsigned char handle[LR_IPC_HANDLE_BYTES], void **dev_ptr);
+LR_API int lr_peer_close(void *dev_ptr);
+LR_API int lr_peer_free(void *dev_ptr);
+
 /* adjoint of lr_drr_forward wrt vol (autograd of sdct:81 / layers.py:187; RegNet2D3D.py:161-185 needs it).
  * grad_vol (B,d,w,h) is ACCUMULATED into (caller zero-initialises). */
 LR_API int lr_drr_backward(const float *grad_proj, int B, int d, int w, int h,

@@ -25,6 +25,11 @@ SIGNATURES = {
     "lr_drr_forward": (_i, [_vp, _i, _i, _i, _i, c_double_p, _i, _i, _i, _i, c_float_p, _i, _f, _vp, _vp]),
     "lr_drr_backward": (_i, [_vp, _i, _i, _i, _i, c_double_p, _i, _i, _i, _i, c_float_p, _i, _f, _vp, _vp]),
     "lr_project_grid": (_i, [c_double_p, _i, _i, _i, _i, _i, _i, c_float_p, _i, _i, _vp, _vp, _vp]),
+    "lr_drr_forward_peers": (_i, [_vp, _i, _i, _i, _i, c_double_p, _i, _i, _i, _i, c_float_p, _i, _f, _vp, _i, _i, _vp]),
+    "lr_peer_alloc": (_i, [_sz, _vp, _vp]),
+    "lr_peer_open": (_i, [_vp, _vp]),
+    "lr_peer_close": (_i, [_vp]),
+    "lr_peer_free": (_i, [_vp]),
     "lr_drr_forward_host_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i]),
     "lr_drr_forward_host": (_i, [_vp, _i, _i, _i, _i, c_double_p, _i, _i, _i, _i, c_float_p, _i, _f, _vp, _vp, _sz, _vp]),
     "lr_backproject_forward": (_i, [_vp, c_float_p, _i, _i, _i, _i, _i, _i, _i, _vp, _i64, _i64, _vp]),

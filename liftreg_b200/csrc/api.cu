@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include <cstring>
 #include "common.cuh"
 
 namespace lr {
@@ -168,6 +169,40 @@ extern "C" int lr_backproject_forward_host(const float *proj_host, const float *
 
 extern "C" int lr_stream_synchronize(lr_stream_t stream) {
     return cuda_ok(cudaStreamSynchronize(as_stream(stream)), "stream_synchronize");
+}
+
+// ---- peer-visible buffers for lr_drr_forward_peers (CUDA IPC between the per-GPU processes of one box) ----------------
+extern "C" int lr_peer_alloc(size_t bytes, void **dev_ptr, unsigned char handle[LR_IPC_HANDLE_BYTES]) {
+    LR_REQUIRE(dev_ptr && handle && bytes > 0, "peer_alloc: null pointer or empty buffer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == LR_IPC_HANDLE_BYTES, "IPC handle size");
+    void *p = nullptr;
+    if (int e = cuda_ok(cudaMalloc(&p, bytes), "peer_alloc: cudaMalloc")) return e;
+    cudaIpcMemHandle_t hd;
+    const cudaError_t ce = cudaIpcGetMemHandle(&hd, p);
+    if (ce != cudaSuccess) {
+        cudaFree(p);
+        return cuda_ok(ce, "peer_alloc: cudaIpcGetMemHandle");
+    }
+    memcpy(handle, &hd, sizeof(hd));
+    *dev_ptr = p;
+    return LR_OK;
+}
+
+extern "C" int lr_peer_open(const unsigned char handle[LR_IPC_HANDLE_BYTES], void **dev_ptr) {
+    LR_REQUIRE(dev_ptr && handle, "peer_open: null pointer");
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, handle, sizeof(hd));
+    return cuda_ok(cudaIpcOpenMemHandle(dev_ptr, hd, cudaIpcMemLazyEnablePeerAccess), "peer_open: cudaIpcOpenMemHandle");
+}
+
+extern "C" int lr_peer_close(void *dev_ptr) {
+    LR_REQUIRE(dev_ptr, "peer_close: null pointer");
+    return cuda_ok(cudaIpcCloseMemHandle(dev_ptr), "peer_close: cudaIpcCloseMemHandle");
+}
+
+extern "C" int lr_peer_free(void *dev_ptr) {
+    LR_REQUIRE(dev_ptr, "peer_free: null pointer");
+    return cuda_ok(cudaFree(dev_ptr), "peer_free: cudaFree");
 }
 
 // ---- warp, host buffers -----------------------------------------------------------------------------

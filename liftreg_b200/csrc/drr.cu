@@ -49,6 +49,13 @@ struct DrrDims {
     int64_t nvox;
 };
 
+// Multi-GPU sweep (lr_drr_forward_peers): the kernel stores every detector pixel into the gather buffers of ALL ranks
+// (peer memory over NVLink), view k of the launch at slot k * vstride, so that no collective moves the images afterwards.
+struct DrrPeers {
+    float *p[LR_MAX_PEERS];
+    int n, vstride;
+};
+
 struct Ray {
     float sx, sy, sz, Dx, Dy, Dz, r2, dx;
     int j0, j1;  // inclusive range of coronal planes that may touch the volume
@@ -202,9 +209,9 @@ __device__ __forceinline__ float finish_ray(float acc, const Ray &r, const DrrDi
 #ifndef LR_DRR_MINB
 #define LR_DRR_MINB 4
 #endif
-template <bool FAST>
+template <bool FAST, bool PEERS>
 __global__ void __launch_bounds__(32 * DRR_PAIRS * DRR_SEGS, LR_DRR_MINB)
-    drr_forward_kernel(const float *__restrict__ vol, float *__restrict__ proj, DrrDims g, DrrViews views) {
+    drr_forward_kernel(const float *__restrict__ vol, float *__restrict__ proj, DrrDims g, DrrViews views, DrrPeers peers) {
     __shared__ float2 part[DRR_SEGS][DRR_PAIRS][32];
     __shared__ Ray rays[DRR_PAIRS][2][32];      // the block's rays, set up once (by the threads of the first two runs)
     const int v = blockIdx.x * 32 + threadIdx.x;
@@ -351,9 +358,22 @@ __global__ void __launch_bounds__(32 * DRR_PAIRS * DRR_SEGS, LR_DRR_MINB)
             ta = add_rn(ta, part[s2][threadIdx.y][threadIdx.x].x);
             tb = add_rn(tb, part[s2][threadIdx.y][threadIdx.x].y);
         }
-        float *out = proj + ((int64_t)(g.view0 + blockIdx.z) * g.rd + ua) * g.rh + v;
-        out[0] = finish_ray(ta, ra, g);
-        if (has_b) out[g.rh] = finish_ray(tb, rb, g);
+        if (PEERS) {
+            const int64_t off = ((int64_t)(g.view0 + blockIdx.z) * peers.vstride * g.rd + ua) * g.rh + v;
+            const float oa = finish_ray(ta, ra, g), ob = finish_ray(tb, rb, g);
+#pragma unroll
+            for (int k = 0; k < LR_MAX_PEERS; ++k) {         // local buffer and the peers' (P2P stores over NVLink)
+                if (k < peers.n) {
+                    float *out = peers.p[k] + off;
+                    out[0] = oa;
+                    if (has_b) out[g.rh] = ob;
+                }
+            }
+        } else {
+            float *out = proj + ((int64_t)(g.view0 + blockIdx.z) * g.rd + ua) * g.rh + v;
+            out[0] = finish_ray(ta, ra, g);
+            if (has_b) out[g.rh] = finish_ray(tb, rb, g);
+        }
     }
 }
 
@@ -556,9 +576,33 @@ extern "C" int lr_drr_forward(const float *vol, int B, int d, int w, int h, cons
     return for_each_view_chunk(poses, n_pose_sets, B, P, [&](int n, const DrrViews &vs, int v0) {
         g.view0 = v0;
         dim3 grid((unsigned)((rh + 31) / 32), (unsigned)((rd + 2 * DRR_PAIRS - 1) / (2 * DRR_PAIRS)), (unsigned)n);
-        if (numerics_mode() == LR_NUMERICS_FAST) drr_forward_kernel<true><<<grid, dim3(32, DRR_PAIRS, DRR_SEGS), 0, as_stream(stream)>>>(vol, proj, g, vs);
-        else drr_forward_kernel<false><<<grid, dim3(32, DRR_PAIRS, DRR_SEGS), 0, as_stream(stream)>>>(vol, proj, g, vs);
+        const DrrPeers none = {};
+        if (numerics_mode() == LR_NUMERICS_FAST) drr_forward_kernel<true, false><<<grid, dim3(32, DRR_PAIRS, DRR_SEGS), 0, as_stream(stream)>>>(vol, proj, g, vs, none);
+        else drr_forward_kernel<false, false><<<grid, dim3(32, DRR_PAIRS, DRR_SEGS), 0, as_stream(stream)>>>(vol, proj, g, vs, none);
         return check_launch("drr_forward_kernel");
+    });
+}
+
+extern "C" int lr_drr_forward_peers(const float *vol, int B, int d, int w, int h, const double *poses, int n_pose_sets, int P,
+                                    int rd, int rh, const float spacing[3], int y_norm_mode, float out_scale,
+                                    float *const *outs, int n_outs, int view_stride, lr_stream_t stream) {
+    LR_REQUIRE(vol && poses && outs, "drr_forward_peers: null pointer");
+    LR_REQUIRE(n_outs >= 1 && n_outs <= LR_MAX_PEERS, "drr_forward_peers: n_outs must be in [1, %d], got %d", LR_MAX_PEERS, n_outs);
+    LR_REQUIRE(view_stride >= 1, "drr_forward_peers: view_stride must be >= 1, got %d", view_stride);
+    DrrPeers peers = {};
+    for (int k = 0; k < n_outs; ++k) {
+        LR_REQUIRE(outs[k], "drr_forward_peers: outs[%d] is null", k);
+        peers.p[k] = outs[k];
+    }
+    peers.n = n_outs; peers.vstride = view_stride;
+    DrrDims g;
+    if (int e = fill_dims(g, B, d, w, h, n_pose_sets, P, rd, rh, spacing, y_norm_mode, out_scale)) return e;
+    return for_each_view_chunk(poses, n_pose_sets, B, P, [&](int n, const DrrViews &vs, int v0) {
+        g.view0 = v0;
+        dim3 grid((unsigned)((rh + 31) / 32), (unsigned)((rd + 2 * DRR_PAIRS - 1) / (2 * DRR_PAIRS)), (unsigned)n);
+        if (numerics_mode() == LR_NUMERICS_FAST) drr_forward_kernel<true, true><<<grid, dim3(32, DRR_PAIRS, DRR_SEGS), 0, as_stream(stream)>>>(vol, nullptr, g, vs, peers);
+        else drr_forward_kernel<false, true><<<grid, dim3(32, DRR_PAIRS, DRR_SEGS), 0, as_stream(stream)>>>(vol, nullptr, g, vs, peers);
+        return check_launch("drr_forward_kernel<peers>");
     });
 }
 

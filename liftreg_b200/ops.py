@@ -124,6 +124,25 @@ def drr_project(vol, poses, resolution, spacing, y_norm_mode=YNORM_WM1, out_scal
     return _DRR.apply(vol, poses, rd, rh, _spacing3(spacing), int(y_norm_mode), float(out_scale), out)
 
 
+def drr_project_peers(vol, poses, resolution, spacing, out_ptrs, view_stride, y_norm_mode=YNORM_WM1, out_scale=0.1):
+    """Multi-GPU sweep form of drr_project (no autograd): the kernel stores the images into every buffer of `out_ptrs`
+    (raw device addresses: this rank's gather buffer and the peers', see sharding.PeerGather), view k of the call at
+    k * view_stride images from each address.  Nothing is returned; the caller orders the ranks with a barrier."""
+    import ctypes
+    poses = _poses64(poses)
+    vol = _need_cuda_f32(vol, "vol")
+    if vol.dim() != 4 or poses.shape[0] not in (1, vol.shape[0]):
+        raise ValueError("vol must be (B,d,w,h) and poses (P,3) or (B,P,3)")
+    B, d, w, h = vol.shape
+    n_sets, P, _ = poses.shape
+    ptrs = (ctypes.c_void_p * len(out_ptrs))(*[int(a) for a in out_ptrs])
+    with torch.cuda.device(vol.device):
+        _native.check(_native.lib().lr_drr_forward_peers(_ptr(vol), B, d, w, h, _dp(poses), n_sets, P, int(resolution[0]),
+                                                         int(resolution[1]), _fp(_spacing3(spacing)), int(y_norm_mode),
+                                                         float(out_scale), ptrs, len(out_ptrs), int(view_stride), _stream()),
+                      "lr_drr_forward_peers")
+
+
 def project_grid(poses, resolution, obj_shape, spacing, device, y_norm_mode=YNORM_WM1, flip=False, want_grid=True):
     """Materialised sample grid (P,rd,rh,w,3) and dx (P,rd,rh) -- reference sdct:15-57, for API parity only."""
     poses = _poses64(poses)[0]

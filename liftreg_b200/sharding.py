@@ -4,9 +4,12 @@ One process per GPU (`torch.distributed`, NCCL over NVLink/NVSwitch on the GPU b
 
   * DRR forward      every ray is independent and needs the whole volume: the (batch x view) list is dealt out to the
                      ranks round-robin (neighbouring views cost the same, so interleaving balances the ranks), the
-                     volume is replicated, and the detector images are all-gathered (0.9 MB at cfg 1, 67 MB at cfg 4:
-                     latency-bound).  Each rank's kernel writes straight into its slot of the gather buffer
-                     (ops.drr_project(out=)), so the collective and the final de-interleave are the only copies.
+                     volume is replicated, and every rank ends up with all detector images.  Two exchange forms:
+                     (a) PeerGather: the DRR kernel itself stores each pixel into the gather buffers of ALL ranks (peer
+                     memory over NVLink, CUDA IPC), in final view order -- no all-gather, no de-interleave, only a
+                     4-byte all-reduce as barrier; (b) NCCL all-gather of per-rank slots (0.9 MB at cfg 1, 67 MB at
+                     cfg 4: latency-bound) + de-interleave, each rank's kernel writing straight into its slot
+                     (ops.drr_project(out=)).  (b) is also what the gloo CPU tests exercise.
   * backprojection   per-voxel gather from tiny, replicated projections: split the output along axis 0 (z-slabs);
                      no halo, no collective (the output stays sharded for the data-parallel consumer).
   * warp             split the OUTPUT along axis 0; phi is sharded like the output, the moving image is replicated
@@ -48,8 +51,114 @@ def interleaved_views(n_views, world, rank):
     return list(range(rank, n_views, world))
 
 
+class _DevicePointer:
+    """Exposes a raw device allocation to torch through __cuda_array_interface__."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 3,
+                                         "strides": None}
+
+
+class PeerGather:
+    """Gather buffers of a view-sharded DRR sweep that the ranks' kernels write directly.
+
+    Every rank allocates `n_buffers` (n_views, rd, rh) float32 buffers with lr_peer_alloc, the CUDA IPC handles are
+    exchanged once through the process group (all_gather_object), and every rank maps every other rank's buffers
+    (lr_peer_open).  A sweep then passes the world's pointers of one buffer to lr_drr_forward_peers: the kernel stores
+    each detector pixel to all of them over NVLink, in final view order.  Two buffers alternate so that a rank may start
+    sweep i+1 while a peer still reads the result of sweep i (a rank enters sweep i+2 only after the barrier of sweep
+    i+1, which every peer enqueues after its reads of sweep i)."""
+
+    def __init__(self, n_views, rd, rh, device, group=None, n_buffers=2):
+        import ctypes
+        from . import _native
+        self.world, self.rank = _world(group)
+        self.group, self.shape, self.device = group, (int(n_views), int(rd), int(rh)), torch.device(device)
+        self._lib, self._ctypes = _native.lib(), ctypes
+        nbytes = 4 * int(n_views) * int(rd) * int(rh)
+        self._own, self._peer, self.ptrs, self.tensors = [], [], [], []
+        with torch.cuda.device(self.device):
+            # every step that can fail is followed by an agreement over the group, so that a failure on one rank raises
+            # on all of them instead of leaving the others inside a collective
+            handles, err = [], None
+            try:
+                for _ in range(n_buffers):
+                    p, hd = ctypes.c_void_p(), (ctypes.c_ubyte * 64)()
+                    _native.check(self._lib.lr_peer_alloc(nbytes, ctypes.byref(p), hd), "lr_peer_alloc")
+                    self._own.append(p.value)
+                    handles.append(bytes(hd))
+            except Exception as e:                           # noqa: BLE001
+                err = "rank %d: %s" % (self.rank, e)
+            everyone = self._agree((handles, err))
+            try:
+                for k in range(n_buffers):
+                    row = []
+                    for r in range(self.world):
+                        if r == self.rank:
+                            row.append(self._own[k])
+                            continue
+                        q = ctypes.c_void_p()
+                        hd = (ctypes.c_ubyte * 64).from_buffer_copy(everyone[r][0][k])
+                        _native.check(self._lib.lr_peer_open(hd, ctypes.byref(q)), "lr_peer_open")
+                        self._peer.append(q.value)
+                        row.append(q.value)
+                    self.ptrs.append(row)
+                    self.tensors.append(torch.as_tensor(_DevicePointer(self._own[k], self.shape), device=self.device))
+            except Exception as e:                           # noqa: BLE001
+                err = "rank %d: %s" % (self.rank, e)
+            self._agree((None, err))
+        self._flag = torch.zeros(1, device=self.device)
+        self._turn = 0
+
+    def _agree(self, item):
+        """all_gather_object of (payload, error); raises on every rank if any rank reported an error."""
+        everyone = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(everyone, item, group=self.group)
+        else:
+            everyone[0] = item
+        errors = [e for _, e in everyone if e]
+        if errors:
+            self._release()
+            raise RuntimeError("PeerGather: " + "; ".join(errors))
+        return everyone
+
+    def _release(self):
+        for q in self._peer:
+            self._lib.lr_peer_close(self._ctypes.c_void_p(q))
+        self._peer, self.tensors = [], []
+        for p in self._own:
+            self._lib.lr_peer_free(self._ctypes.c_void_p(p))
+        self._own = []
+
+    def next_buffer(self):
+        k = self._turn
+        self._turn = (self._turn + 1) % len(self.tensors)
+        return self.tensors[k], self.ptrs[k]
+
+    def barrier(self):
+        """Stream-ordered rendezvous of the ranks (a 4-byte all-reduce): after it, every rank's stores of this sweep are
+        complete and visible."""
+        if self.world > 1:
+            dist.all_reduce(self._flag, group=self.group)
+
+    def close(self):
+        """Collective: unmap the peers' buffers, then free the own ones."""
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize()
+            for q in self._peer:
+                self._lib.lr_peer_close(self._ctypes.c_void_p(q))
+            self._peer = []
+            if self.world > 1:
+                dist.barrier(group=self.group)
+            self.tensors = []
+            for p in self._own:
+                self._lib.lr_peer_free(self._ctypes.c_void_p(p))
+            self._own = []
+
+
 def drr_project_sharded(vol, poses, resolution, spacing, y_norm_mode=0, out_scale=0.1, group=None, gather=True,
-                        project_fn=None, buf=None):
+                        project_fn=None, buf=None, peers=None):
     """View-sharded DRR.  vol (B,d,w,h) replicated on every rank; poses (P,3) or (B,P,3).
 
     The flattened list of (b,p) views is dealt out to the ranks round-robin (view v -> rank v % world); each rank
@@ -60,6 +169,8 @@ def drr_project_sharded(vol, poses, resolution, spacing, y_norm_mode=0, out_scal
     to the CUDA op, which writes each rank's images directly into its slot of the gather buffer (`out=`), so the
     collective is the only copy besides the final de-interleave; the CPU tests inject the oracle (whose result is copied in).
     `buf`: optional pre-allocated (world, slot, rd, rh) gather buffer (benchmarks reuse it across calls).
+    `peers`: a PeerGather for (B*P, rd, rh): the kernel stores into every rank's buffer directly and the full result is
+    returned as a view of this rank's buffer (valid until the sweep after the next one); no all-gather, no de-interleave.
     """
     native = project_fn is None
     if native:
@@ -73,6 +184,26 @@ def drr_project_sharded(vol, poses, resolution, spacing, y_norm_mode=0, out_scal
     P = p64.shape[1]
     rd, rh = int(resolution[0]), int(resolution[1])
     n_views = B * P
+    if peers is not None:
+        if not native or not gather:
+            raise ValueError("peers= needs the CUDA op and gather=True")
+        if peers.shape != (n_views, rd, rh) or peers.world != world:
+            raise ValueError("PeerGather is for %s on %d ranks" % (peers.shape, peers.world))
+        from . import ops
+        local, ptrs = peers.next_buffer()
+        my_views = interleaved_views(n_views, world, rank)
+        i = 0
+        while i < len(my_views):                            # one launch per batch item, as below
+            b = my_views[i] // P
+            k = i
+            while k < len(my_views) and my_views[k] // P == b:
+                k += 1
+            ps = np.ascontiguousarray(p64[b, [v - b * P for v in my_views[i:k]]])
+            first = 4 * my_views[i] * rd * rh               # byte offset of this launch's first view in every buffer
+            ops.drr_project_peers(vol[b:b + 1], ps, (rd, rh), spacing, [a + first for a in ptrs], world, y_norm_mode, out_scale)
+            i = k
+        peers.barrier()
+        return local.view(B, P, rd, rh)
     slot = (n_views + world - 1) // world                 # all_gather needs equal-sized contributions
     if buf is None:
         buf = torch.zeros((world, slot, rd, rh), device=vol.device, dtype=torch.float32)

@@ -208,6 +208,31 @@ def test_proj_layer_forward_backward_vs_reference_golden(dev):
         assert rel_l2(x.grad[b].cpu().numpy(), g["grad_x"][b]) <= GRAD_TOL
 
 
+def test_drr_peer_store_form_single_gpu(dev):
+    """lr_drr_forward_peers: the kernel stores each image into several buffers, view k at k * view_stride images (what the
+    view-sharded sweep uses to fill every rank's gather buffer in final view order); here both 'peers' are local."""
+    from liftreg_b200 import ops, sharding, synthetic
+    rs = np.random.RandomState(12)
+    shape, res, P = (14, 12, 18), (21, 37), 5
+    vol = cu(rs.rand(1, *shape).astype(np.float32), dev)
+    poses = synthetic.wrapper_poses(60.0, P, shape[1])
+    ref = ops.drr_project(vol, poses, res, (2.2, 2.2, 2.2))
+    # views 1 and 3 of 5 with stride 2 into two zeroed (5,rd,rh) buffers, starting at view 1
+    a, b = torch.zeros((P,) + res, device=dev), torch.zeros((P,) + res, device=dev)
+    first = 4 * 1 * res[0] * res[1]
+    ops.drr_project_peers(vol, poses[[1, 3]], res, (2.2, 2.2, 2.2), [a.data_ptr() + first, b.data_ptr() + first], 2)
+    want = torch.zeros_like(a)
+    want[1], want[3] = ref[0, 1], ref[0, 3]
+    assert torch.equal(a, want) and torch.equal(b, want)
+    # PeerGather on one rank: same code path as the multi-GPU sweep (IPC allocation, alternating buffers)
+    pg = sharding.PeerGather(P, res[0], res[1], dev)
+    for _ in range(3):
+        assert torch.equal(sharding.drr_project_sharded(vol, poses, res, (2.2, 2.2, 2.2), peers=pg), ref)
+    pg.close()
+    with pytest.raises(Exception):
+        ops.drr_project_peers(vol, poses, res, (2.2, 2.2, 2.2), [a.data_ptr()] * 9, 1)      # more than LR_MAX_PEERS
+
+
 def test_drr_backward_vs_oracle_and_adjoint_identity(dev):
     from liftreg_b200 import ops, synthetic
     from oracle import c_oracle

@@ -34,6 +34,16 @@ def _worker(rank, world, port, q):
         full = sharding.drr_project_sharded(vol, poses, (36, 40), (2.2, 2.2, 2.2))        # view-sharded + all-gather
         ref = ops.drr_project(vol, poses, (36, 40), (2.2, 2.2, 2.2))
         ok_drr = bool(torch.equal(full, ref))
+        # the same sweep with the kernels storing into every rank's buffer over NVLink (no all-gather): three sweeps,
+        # so that both alternating buffers and the reuse of the first one are exercised, with different volumes
+        pg = sharding.PeerGather(2 * 5, 36, 40, dev)
+        ok_peer = True
+        for it in range(3):
+            vol_it = vol * (1.0 + 0.25 * it)
+            got = sharding.drr_project_sharded(vol_it, poses, (36, 40), (2.2, 2.2, 2.2), peers=pg)
+            ok_peer = ok_peer and bool(torch.equal(got, ops.drr_project(vol_it, poses, (36, 40), (2.2, 2.2, 2.2))))
+        pg.close()
+        ok_drr = ok_drr and ok_peer
         tp = torch.from_numpy(rs.uniform(-1, 1, (2, 5, 40, 44)).astype(np.float32)).to(dev)
         shape = (25, 20, 28)
         fullv, _ = sharding.backproject_sharded(tp, poses.astype(np.float32), shape, gather=True)
