@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """BASELINE.json configs[3]: DRR generation sweep -- 512^3 CT, 64 views over 60 deg, 512^2 detector, view-sharded across
-the GPUs of one box with an NCCL all-gather of the detector images (liftreg_b200.sharding.drr_project_sharded).
+the GPUs of one box (liftreg_b200.sharding.drr_project_sharded); the detector images reach every rank either through P2P
+stores from the DRR kernel (sharding.PeerGather), through an NCCL all-gather, or stay sharded.
 
     python tools/drr_sweep.py                                                   # 1 GPU
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 tools/drr_sweep.py
@@ -35,16 +36,19 @@ def main():
     tv = torch.from_numpy(vol[None]).to(dev)                       # replicated volume (537 MB)
     poses = synthetic.wrapper_poses(60.0, P, n)
     reps = 5
-    for gather in (True, False):
+    pg = sharding.PeerGather(P, det[0], det[1], dev)
+    for exchange in ("p2p_stores", "nccl_all_gather", "none"):
+        gather = exchange != "none"
+        kw = {"peers": pg} if exchange == "p2p_stores" else {"gather": gather}
         for _ in range(2):
-            out = sharding.drr_project_sharded(tv, poses, det, (1.0, 1.0, 1.0), gather=gather)
+            out = sharding.drr_project_sharded(tv, poses, det, (1.0, 1.0, 1.0), **kw)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(reps):
-            out = sharding.drr_project_sharded(tv, poses, det, (1.0, 1.0, 1.0), gather=gather)
+            out = sharding.drr_project_sharded(tv, poses, det, (1.0, 1.0, 1.0), **kw)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
@@ -56,8 +60,9 @@ def main():
             nominal = P * det[0] * det[1] * n
             full = out if gather else out[0]          # (gather=False: this rank's images and its view list)
             print(json.dumps({"workload": "cfg4: DRR sweep 512^3, 64 views / 60 deg, 512^2 detector", "n_gpus": world,
-                              "all_gather": gather, "ms_per_sweep": ms, "nominal_ray_samples": nominal,
+                              "exchange": exchange, "ms_per_sweep": ms, "nominal_ray_samples": nominal,
                               "samples_per_s": nominal / ms * 1e3, "checksum": float(full.double().sum().item())}))
+    pg.close()
     if world > 1:
         dist.destroy_process_group()
 
