@@ -296,8 +296,9 @@ class GraphSteps:
     graph); beyond that, n // CHUNK replays of a CHUNK-step graph plus one graph of the remainder."""
     CHUNK = 256
 
-    def __init__(self, b, fn, R):
+    def __init__(self, b, fn, R, begin=None, end=None):
         self.b, self.fn, self.R, self.graphs = b, fn, R, {}
+        self.begin, self.end = begin, end                    # optional hooks around the captured steps (fork / join)
         torch = b.torch
         with torch.cuda.stream(b.stream):
             fn(0, b.st)                                      # module load / first-launch outside capture
@@ -309,8 +310,12 @@ class GraphSteps:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.stream(b.stream):
                 with torch.cuda.graph(g, stream=b.stream):
+                    if self.begin:
+                        self.begin()
                     for r in range(n):
                         self.fn(r % self.R, b.st)
+                    if self.end:
+                        self.end()
             self.graphs[n] = g
         return self.graphs[n]
 
@@ -383,8 +388,34 @@ def section_headline(b, target_proj, moving, phi, poses32):
         k_warp(r, st)
         join = torch.cuda.Event(); join.record(b.side); b.stream.wait_event(join)
 
+    # The backprojection and the warp of a step are independent (in the model the encoder sits between them), and so are
+    # consecutive steps (rotating buffer sets).  Default: the K backprojections run back to back on one stream and the K
+    # warps on another, forked at the start of the graph and joined at its end, so one kernel's ramp-up and drain overlap
+    # the other kernel's steady state (37.0 us per step; with a fork and a join inside EVERY step, LIFTREG_BENCH_CHAINS=0,
+    # 39.4 us; more than one chain per kernel changes nothing).
+    n_chains = int(os.environ.get("LIFTREG_BENCH_CHAINS", "1"))
+    extra = [torch.cuda.Stream(device=dev) for _ in range(max(0, 2 * n_chains - 2))]
+    bp_streams = ([b.side] + extra[:n_chains - 1]) if n_chains else []
+    warp_streams = ([b.stream] + extra[n_chains - 1:]) if n_chains else []
+
+    def chains_begin():
+        fork = torch.cuda.Event(); fork.record(b.stream)
+        for s_ in bp_streams + warp_streams[1:]:
+            s_.wait_event(fork)
+
+    def step_chained(r, st):
+        k_backproject(r, ctypes.c_void_p(bp_streams[r % n_chains].cuda_stream))
+        k_warp(r, ctypes.c_void_p(warp_streams[r % n_chains].cuda_stream))
+
+    def chains_end():
+        for s_ in bp_streams + warp_streams[1:]:
+            join = torch.cuda.Event(); join.record(s_); b.stream.wait_event(join)
+
     native.launch_count_reset()
-    g_step = GraphSteps(b, step_forked, R)
+    if n_chains:
+        g_step = GraphSteps(b, step_chained, R, begin=chains_begin, end=chains_end)
+    else:
+        g_step = GraphSteps(b, step_forked, R)
     launches_per_step = native.launch_count()                     # the constructor ran exactly one step eagerly
     g_bp, g_warp, g_wb = GraphSteps(b, k_backproject, R), GraphSteps(b, k_warp, R), GraphSteps(b, k_warp_bwd, R)
 
@@ -857,14 +888,22 @@ def run_b200(args):
             "config": workload_config(
                 world, l2="rotating %d buffer sets (%.0f MB) > 126 MB L2; no flush kernel" % (ROTATION, ROTATION * 148.5),
                 launch="CUDA graphs of exactly `steps` steps (one graph up to %d steps, else that graph replayed + one graph of the "
-                       "remainder; nothing launched eagerly); inside a step the two independent kernels run as parallel graph "
-                       "branches on two streams and join" % GraphSteps.CHUNK,
+                       "remainder; nothing launched eagerly); the K backprojections and the K warps are two independent chains of "
+                       "graph nodes on two streams (forked at the start of the graph, joined at its end; "
+                       "LIFTREG_BENCH_CHAINS=0: fork and join inside every step)" % GraphSteps.CHUNK,
                 numerics="%s (lr_set_numerics; indices and weights bit-exact in both modes)" % b.native.get_numerics(),
                 host="%d cpus; %s" % (os.cpu_count(), b.numa)),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbps"], "peak": peak, "unit": "GB/s",
                          "frac": kern[dom]["gbps"] / peak, "traffic": traffic.get(dom), "peak_source": peak_src,
                          "traffic_source": traffic.get("_how"),
                          "algorithmic_bytes_per_launch": kern[dom]["bytes"], "us_per_launch": kern[dom]["us"]},
+            # the step as it runs (both kernels concurrently as graph branches): algorithmic bytes of the two launches over
+            # the step time -- per GPU, so comparable with `peak` at any N
+            "step_roofline": (lambda nbytes: {"bound": "hbm", "achieved": nbytes / (ms_per_step * 1e-3) * 1e-9, "peak": peak,
+                                              "unit": "GB/s", "frac": nbytes / (ms_per_step * 1e-3) * 1e-9 / peak,
+                                              "algorithmic_bytes_per_step": nbytes,
+                                              "what": "backprojection + warp launches of one step, overlapped on one GPU"})(
+                kern["backproject_forward_kernel"]["bytes"] + kern["warp_forward_kernel"]["bytes"]),
             "kernels": kern,
             "drr_forward_cfg1": {k: (dict(v, frac_of_hbm_peak_compulsory=v["gbps_compulsory"] / peak) if "gbps_compulsory" in v else v)
                                  for k, v in drr_extra.items()},
