@@ -290,11 +290,14 @@ __global__ void __launch_bounds__(NCC_THREADS, LR_REGP_MINB) diffusion_reg_pair_
         const unsigned pl = (unsigned)(g.h * g.w), cs = pl * (unsigned)g.d;
         unsigned i0 = ((unsigned)b * 3u * (unsigned)g.d + (unsigned)z0) * pl + (unsigned)y * (unsigned)g.w + (unsigned)x;
         const f32x2 sd2 = splat2(g.sd), sh2 = splat2(g.sh), sw2 = splat2(g.sw);
+#ifndef LR_REG_WINDOW
+#define LR_REG_WINDOW 1
+#endif
         f32x2 vm[3], vc[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            vc[c] = ldg2(disp + (i0 + c * cs));
-            vm[c] = z0 > 0 ? ldg2(disp + (i0 + c * cs - pl)) : vc[c];
+            vc[c] = LR_REG_WINDOW ? ldg2(disp + (i0 + c * cs)) : 0ull;
+            vm[c] = LR_REG_WINDOW ? (z0 > 0 ? ldg2(disp + (i0 + c * cs - pl)) : vc[c]) : 0ull;
         }
         f32x2 part = 0ull;                                               // fp32 partial sums of at most 16 planes
         for (int z = z0; z < z1; ++z, i0 += pl) {
@@ -303,7 +306,8 @@ __global__ void __launch_bounds__(NCC_THREADS, LR_REGP_MINB) diffusion_reg_pair_
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 const unsigned ic = i0 + c * cs;
-                const f32x2 cc = vc[c];
+                const f32x2 cc = LR_REG_WINDOW ? vc[c] : ldg2(disp + ic);
+                if (!LR_REG_WINDOW) vm[c] = zlo ? cc : ldg2(disp + (ic - pl));
                 const f32x2 vp = zhi ? cc : ldg2(disp + (ic + pl));      // allocating load: next iteration's row neighbours hit L1
                 if (LR_REG_PF > 0 && z + LR_REG_PF <= z1) prefetch_l2(disp + (ic + LR_REG_PF * pl));
                 const f32x2 yu = ldg2(disp + (ic + oyu)), yd = ldg2(disp + (ic + oyd));
@@ -335,7 +339,7 @@ __global__ void __launch_bounds__(NCC_THREADS, LR_REGP_MINB) diffusion_reg_pair_
             }
         }
     }
-    block_accumulate_f64(acc, sum);
+    block_accumulate_f64(acc, sum);      // one fp64 atomic per block (spreading them over 64 addresses changed nothing)
 }
 
 // x term of the adjoint for the pair (x, x+1): interior (I_p - I_{p-2}) - (I_{p+2} - I_p); the first pair of a row sees

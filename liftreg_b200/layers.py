@@ -49,4 +49,6 @@ class proj_layer(nn.Module):
 
     def forward(self, x):
         x_proj = ops.drr_project(x, self.emi_poses, self.proj_resolution, self.spacing, ops.YNORM_W, out_scale=1.0)
-        return F.interpolate(x_proj, self.out_shape)        # :190 (nearest)
+        if tuple(int(v) for v in self.out_shape) == tuple(x_proj.shape[2:]):
+            return x_proj                                   # nearest resize to the same size is the identity
+        return F.interpolate(x_proj, self.out_shape)        # :190 (nearest): the one stock-torch op left on this layer
