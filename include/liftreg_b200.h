@@ -275,6 +275,8 @@ LR_API int lr_backproject_forward_plan(int B, int P, int pw, int ph, int d, int 
 LR_API int lr_probe_l1_gather(const float *buf, int64_t buf_floats, int blocks, int floats_per_block, int iters,
                               float *sink, lr_stream_t stream);
 LR_API int lr_probe_issue(int blocks, int iters, float *sink, lr_stream_t stream);
+/* lr_probe_issue_packed: the same with packed fp32x2 FMAs (blocks*256 threads, iters*8 FFMA2 each). */
+LR_API int lr_probe_issue_packed(int blocks, int iters, float *sink, lr_stream_t stream);
 
 /* ---- similarity loss on the warp output -------------- */
 /* replaces src/liftreg/layers/losses.py:14-29 NCCLoss.forward (training similarity, SubspaceLoss.py:27; validation score,

@@ -58,6 +58,7 @@ SIGNATURES = {
     "lr_backproject_forward_plan": (_i, [_i, _i, _i, _i, _i, _i, _i, ctypes.POINTER(ctypes.c_int)]),
     "lr_probe_l1_gather": (_i, [_vp, _i64, _i, _i, _i, _vp, _vp]),
     "lr_probe_issue": (_i, [_i, _i, _vp, _vp]),
+    "lr_probe_issue_packed": (_i, [_i, _i, _vp, _vp]),
     "lr_ncc_sums": (_i, [_vp, _vp, _i, _i64, _vp, _vp]),
     "lr_ncc_backward": (_i, [_vp, _vp, _i, _i64, _vp, _vp, _vp, _vp]),
     "lr_diffusion_reg_sum": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),

@@ -43,6 +43,26 @@ __global__ void __launch_bounds__(256) probe_issue_kernel(int iters, float a, fl
     if (s == 123.456f) sink[0] = s;
 }
 
+// The same with packed fp32x2 FMAs (FFMA2): tells whether a packed instruction costs one or two FP32-pipe cycles.
+__global__ void __launch_bounds__(256) probe_issue_packed_kernel(int iters, float a, float *__restrict__ sink) {
+    f32x2 acc[8];
+    const f32x2 a2 = splat2(a), one = splat2(1.0f);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc[u] = pack2((float)(threadIdx.x + u), (float)(threadIdx.x - u));
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[u] = fma2(acc[u], a2, one);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        float lo, hi;
+        unpack2(acc[u], lo, hi);
+        s += lo + hi;
+    }
+    if (s == 123.456f) sink[0] = s;
+}
+
 }  // namespace lr
 
 using namespace lr;
@@ -61,4 +81,10 @@ extern "C" int lr_probe_issue(int blocks, int iters, float *sink, lr_stream_t st
     LR_REQUIRE(sink && blocks > 0 && iters > 0, "probe_issue: bad argument");
     probe_issue_kernel<<<blocks, 256, 0, as_stream(stream)>>>(iters, 0.999f, sink);
     return check_launch("probe_issue_kernel");
+}
+
+extern "C" int lr_probe_issue_packed(int blocks, int iters, float *sink, lr_stream_t stream) {
+    LR_REQUIRE(sink && blocks > 0 && iters > 0, "probe_issue_packed: bad argument");
+    probe_issue_packed_kernel<<<blocks, 256, 0, as_stream(stream)>>>(iters, 0.999f, sink);
+    return check_launch("probe_issue_packed_kernel");
 }
