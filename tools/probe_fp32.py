@@ -1,5 +1,12 @@
+#!/usr/bin/env python
+"""Scalar FFMA vs packed fp32x2 FFMA2 instruction throughput on the current GPU (lr_probe_issue / lr_probe_issue_packed).
+
+    python tools/probe_fp32.py
+
+B200: 3.67 scalar FFMA and 1.98 FFMA2 per clock per SM -- a packed instruction holds the FP32 pipe for two cycles."""
 import ctypes, sys
-sys.path.insert(0, '.')
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from liftreg_b200 import _native
 lib = _native.lib()
