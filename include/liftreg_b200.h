@@ -282,7 +282,7 @@ LR_API int lr_probe_issue_packed(int blocks, int iters, float *sink, lr_stream_t
 /* replaces src/liftreg/layers/losses.py:14-29 NCCLoss.forward (training similarity, SubspaceLoss.py:27; validation score,
  * RegistrationNet.py:210-212):  a = x - mean(x) + 1e-10, b = y - mean(y) + 1e-10 per batch item over N voxels,
  * ncc = mean(a*b) / sqrt(mean(a*a) * mean(b*b)).
- * lr_ncc_sums fills sums (B,7) float64, device memory owned by the caller (zeroed by the call):
+ * lr_ncc_sums (one pass over x and y) fills sums (B,7) float64, device memory owned by the caller (zeroed by the call):
  *   [sum x, sum y, sum a*b, sum a*a, sum b*b, sum a, sum b]  ->  ncc_b = s2 / sqrt(s3*s4); loss = 1 - mean_b ncc_b.
  * lr_ncc_backward: grad_x (B,N) = d(loss)/dx * grad_loss[0] (grad_loss: one float in device memory), from the same sums. */
 LR_API int lr_ncc_sums(const float *x, const float *y, int B, int64_t N, double *sums, lr_stream_t stream);

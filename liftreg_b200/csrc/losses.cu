@@ -5,8 +5,9 @@
 //     a = x - mean(x) + 1e-10,  b = y - mean(y) + 1e-10                       (per batch item, over all voxels)
 //     ncc = mean(a*b) / sqrt(mean(a^2) * mean(b^2)),   loss = 1 - mean_over_batch(ncc)
 // The reference runs ~10 elementwise / reduction kernels over the two volumes (each re-reading 16 MB per item at 160^3);
-// here the forward is two passes over x and y (sums, then centred second moments: the centring needs the means first)
-// and the backward is one pass.  Per-thread partial sums are fp32 over a handful of elements, everything above that
+// here the forward is ONE pass over x and y (raw moments about the item's first voxel, rewritten into the centred ones by a
+// B-thread kernel; the two-pass op-for-op form -- sums, then fp32-centred second moments -- stays behind
+// LIFTREG_B200_NCC_TWO_PASS=1) and the backward is one pass.  Per-thread partial sums are fp32 over a handful of elements, everything above that
 // is accumulated in fp64 (warp shuffles, shared memory, one fp64 atomic per block), so the result does not depend on the launch shape
 // beyond fp64 round-off.
 #include "common.cuh"
@@ -73,6 +74,44 @@ __global__ void __launch_bounds__(NCC_THREADS) ncc_moment_kernel(const float *__
     }
     const float v[5] = {sab, saa, sbb, sa, sb};
     block_accumulate<5>(v, sums + b * NCC_SUMS + 2);
+}
+
+// Single-pass forward.  The centring needs the means, which is why the restatement above reads x and y twice; but with
+// u = x - k, v = y - l for ANY constants k, l the centred moments follow from the raw moments of u and v:
+//     a = x - mean + eps = u - dx  (dx = mean - k - eps)   =>   sum a*a = sum u*u - 2 dx sum u + N dx^2, etc.
+// and the cancellation in these differences is mild when k, l lie within a few standard deviations of the means.  k and l are
+// the item's first voxels (every thread reads them); per-thread fp32 partials over a few elements, everything above in fp64
+// as before; a B-thread kernel then rewrites the five raw sums into the seven-entry layout the backward and the host use.
+// What is not reproduced is the reference's fp32 rounding of each (x - mean) + 1e-10 (the 1e-10 is below half an ulp of all
+// but the elements within 1e-3 of the mean): the loss differs from the two-pass kernels by ~1e-8.
+__global__ void __launch_bounds__(NCC_THREADS) ncc_shifted_kernel(const float *__restrict__ x, const float *__restrict__ y, int64_t N,
+                                                                  double *__restrict__ sums) {
+    const int b = blockIdx.y;
+    const float *xb = x + (int64_t)b * N, *yb = y + (int64_t)b * N;
+    const float k = __ldg(xb), l = __ldg(yb);
+    float su = 0.0f, sv = 0.0f, suv = 0.0f, suu = 0.0f, svv = 0.0f;
+    for (int64_t i = (int64_t)blockIdx.x * NCC_THREADS + threadIdx.x; i < N; i += (int64_t)gridDim.x * NCC_THREADS) {
+        const float u = ld_stream(xb + i) - k, v = ld_stream(yb + i) - l;
+        su += u; sv += v;
+        suv = fmaf(u, v, suv); suu = fmaf(u, u, suu); svv = fmaf(v, v, svv);
+    }
+    const float vals[5] = {su, sv, suv, suu, svv};
+    block_accumulate<5>(vals, sums + b * NCC_SUMS);
+}
+
+__global__ void ncc_finalize_kernel(const float *__restrict__ x, const float *__restrict__ y, int64_t N, int B, double *__restrict__ sums) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double *s = sums + b * NCC_SUMS;
+    const double n = (double)N, k = (double)x[(int64_t)b * N], l = (double)y[(int64_t)b * N];
+    const double Su = s[0], Sv = s[1], Suv = s[2], Suu = s[3], Svv = s[4];
+    const double Sx = Su + n * k, Sy = Sv + n * l;
+    const double dx = (double)(float)(Sx / n) - k, dy = (double)(float)(Sy / n) - l;      // the means as the fp32 values the backward uses
+    s[0] = Sx; s[1] = Sy;
+    s[2] = Suv - dy * Su - dx * Sv + n * dx * dy;
+    s[3] = Suu - 2.0 * dx * Su + n * dx * dx;
+    s[4] = Svv - 2.0 * dy * Sv + n * dy * dy;
+    s[5] = Su - n * dx; s[6] = Sv - n * dy;
 }
 
 // backward wrt x:  ncc = Sab / sqrt(Saa Sbb);  d ncc / d a_i = c1 b_i - c2 a_i  with c1 = 1/sqrt(Saa Sbb),
@@ -453,6 +492,14 @@ extern "C" int lr_ncc_sums(const float *x, const float *y, int B, int64_t N, dou
     cudaError_t ce = cudaMemsetAsync(sums, 0, sizeof(double) * NCC_SUMS * (size_t)B, st);
     if (ce != cudaSuccess) { set_error("ncc_sums: memset failed: %s", cudaGetErrorString(ce)); return LR_ERR_CUDA; }
     const dim3 grid(ncc_blocks(N, B), (unsigned)B);
+    // LIFTREG_B200_NCC_TWO_PASS=1: the op-for-op restatement (means first, then the fp32-centred moments)
+    static const bool two_pass = [] { const char *e = getenv("LIFTREG_B200_NCC_TWO_PASS"); return e && e[0] == '1'; }();
+    if (!two_pass) {
+        ncc_shifted_kernel<<<grid, NCC_THREADS, 0, st>>>(x, y, N, sums);
+        if (int e = check_launch("ncc_shifted_kernel")) return e;
+        ncc_finalize_kernel<<<(B + 127) / 128, 128, 0, st>>>(x, y, N, B, sums);
+        return check_launch("ncc_finalize_kernel");
+    }
     ncc_sum_kernel<<<grid, NCC_THREADS, 0, st>>>(x, y, N, sums);
     if (int e = check_launch("ncc_sum_kernel")) return e;
     ncc_moment_kernel<<<grid, NCC_THREADS, 0, st>>>(x, y, N, sums);

@@ -14,7 +14,7 @@ from . import ops
 
 
 class NCCLoss(nn.Module):
-    """1 - mean_b NCC(input_b, target_b), reference layers/losses.py:14-29; two fused passes instead of ~10 kernels."""
+    """1 - mean_b NCC(input_b, target_b), reference layers/losses.py:14-29; one fused pass instead of ~10 kernels."""
 
     def forward(self, input, target):
         loss = ops.ncc_loss(input.reshape(input.shape[0], -1), target.reshape(target.shape[0], -1))

@@ -889,7 +889,7 @@ def test_cfg5_training_step_ops_batch4_forward_backward(dev):
 
 # ------------------------------------------------------------------ row f4: similarity loss and label warp
 def test_ncc_loss_vs_reference_golden(dev):
-    """NCCLoss mirror (two fused passes + one backward pass) against the reference's value and gradient; fp32 tolerance:
+    """NCCLoss mirror (one fused forward pass + one backward pass) against the reference's value and gradient; fp32 tolerance:
     the reference sums in torch's fp32 cascade, the kernels in fp32 partials + fp64."""
     from liftreg_b200 import losses
     g = load_golden("ncc")

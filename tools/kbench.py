@@ -106,7 +106,7 @@ def main():
     ncc_sums = torch.zeros((1, 7), device=dev, dtype=torch.float64)
     ncc_g = torch.ones(1, device=dev)
 
-    def k_ncc(s, st):          # forward of the similarity loss: two passes over warped + target
+    def k_ncc(s, st):          # forward of the similarity loss: one pass over warped + target (+ memset and a B-thread finalisation)
         _native.check(lib.lr_ncc_sums(vp(s["warped"]), vp(s["moving"]), 1, nv, vp(ncc_sums), st), "ncc")
 
     def k_ncc_bwd(s, st):
@@ -120,7 +120,7 @@ def main():
     def k_reg_bwd(s, st):
         _native.check(lib.lr_diffusion_reg_backward(vp(s["phi"]), 1, *VOL, 0, vp(ncc_g), vp(s["gphi"]), st), "reg_bwd")
 
-    units = {"reg": (k_reg, nv, 12 * nv), "reg_bwd": (k_reg_bwd, nv, 24 * nv), "ncc": (k_ncc, nv, 16 * nv), "ncc_bwd": (k_ncc_bwd, nv, 12 * nv), "warp": (k_warp, batch * nv, batch * 20 * nv), "pca": (k_pca, 3 * nv, 4 * 3 * nv * 56 + 8 * 3 * nv),
+    units = {"reg": (k_reg, nv, 12 * nv), "reg_bwd": (k_reg_bwd, nv, 24 * nv), "ncc": (k_ncc, nv, 8 * nv), "ncc_bwd": (k_ncc_bwd, nv, 12 * nv), "warp": (k_warp, batch * nv, batch * 20 * nv), "pca": (k_pca, 3 * nv, 4 * 3 * nv * 56 + 8 * 3 * nv),
              "pca_bwd": (k_pca_bwd, 3 * nv, 4 * 3 * nv * 56 + 4 * 3 * nv), "warp_bwd": (k_warp_bwd, nv, 32 * nv),
              "drr_bwd": (k_drr_bwd, P * 240 * 240 * VOL[1], 4 * nv + 4 * P * 240 * 240), "backproject": (k_backproject, batch * P * nv, batch * (4 * P * nv + 4 * P * DET[0] * DET[1])),
              "backproject_planned": (k_backproject_planned, batch * P * nv, batch * (4 * P * nv + 4 * P * DET[0] * DET[1])),
