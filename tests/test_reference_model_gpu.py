@@ -51,9 +51,21 @@ target_proj = np.stack([np.roll(tp0, 2 * b, axis=1 + b %% 2) * (1.0 - 0.05 * b) 
 inp = {"source": torch.from_numpy(moving).to(dev), "target": torch.from_numpy(moving[::-1].copy()).to(dev),
        "target_proj": torch.from_numpy(target_proj.astype(np.float32)).to(dev),
        "target_poses": torch.from_numpy(np.repeat(poses[None], B, 0).astype(np.float32))}
+def timed_forward(model):
+    """ms of one more forward (the first call built caches / picked conv algorithms), CUDA events."""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    with torch.no_grad():
+        model(inp)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1)
+
 with torch.no_grad():
     out_ref = ref(inp)
 want = {k: out_ref[k].float().cpu() for k in ("warped", "phi", "params", "pca_coefs")}
+ms_reference_cuda = min(timed_forward(ref) for _ in range(3))
 state = ref.state_dict()
 del ref, out_ref
 torch.cuda.empty_cache()
@@ -70,7 +82,8 @@ for mode in ("exact", "fast"):
     with torch.no_grad():
         out = m(inp)
     torch.cuda.synchronize()
-    r = {"launches": _native.launch_count(), "basis_contiguous": bool(m.pca_vectors.is_contiguous())}
+    r = {"launches": _native.launch_count(), "basis_contiguous": bool(m.pca_vectors.is_contiguous()),
+         "ms_forward": min(timed_forward(m) for _ in range(3)), "ms_forward_reference_cuda": ms_reference_cuda}
     for k, w in want.items():
         o = out[k].float().cpu()
         num = (o.double() - w.double()).reshape(B, -1).norm(dim=1)
@@ -92,6 +105,9 @@ def test_cfg3_real_reference_model_forward_with_dropin_batch8():
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
     line = [l for l in out.stdout.splitlines() if l.startswith("RESULT ")][-1]
     res = json.loads(line[len("RESULT "):])
+    if os.environ.get("LIFTREG_B200_TIMING_OUT"):        # full-model forward times of this run (stock torch CUDA ops vs drop-in)
+        with open(os.environ["LIFTREG_B200_TIMING_OUT"], "w") as f:
+            json.dump(res, f, indent=1)
     for mode in ("exact", "fast"):
         r = res[mode]
         assert r["launches"] >= 3, r                     # backprojection, PCA decode, warp ran in the native library
