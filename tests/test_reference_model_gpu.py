@@ -84,6 +84,19 @@ for mode in ("exact", "fast"):
     torch.cuda.synchronize()
     r = {"launches": _native.launch_count(), "basis_contiguous": bool(m.pca_vectors.is_contiguous()),
          "ms_forward": min(timed_forward(m) for _ in range(3)), "ms_forward_reference_cuda": ms_reference_cuda}
+    xin = torch.randn((B, 1 + P) + shape, device=dev)      # the conv encoder + FC alone (the reference's own modules, both runs)
+    def encoder_ms():
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record()
+        with torch.no_grad():
+            x = xin
+            for enc in m.encoders:
+                x = enc(x)
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+    encoder_ms()
+    r["ms_encoder_alone"] = min(encoder_ms() for _ in range(3))
+    del xin
     for k, w in want.items():
         o = out[k].float().cpu()
         num = (o.double() - w.double()).reshape(B, -1).norm(dim=1)
