@@ -120,7 +120,13 @@ def main():
     def k_reg_bwd(s, st):
         _native.check(lib.lr_diffusion_reg_backward(vp(s["phi"]), 1, *VOL, 0, vp(ncc_g), vp(s["gphi"]), st), "reg_bwd")
 
-    units = {"reg": (k_reg, nv, 12 * nv), "reg_bwd": (k_reg_bwd, nv, 24 * nv), "ncc": (k_ncc, nv, 8 * nv), "ncc_bwd": (k_ncc_bwd, nv, 12 * nv), "warp": (k_warp, batch * nv, batch * 20 * nv), "pca": (k_pca, 3 * nv, 4 * 3 * nv * 56 + 8 * 3 * nv),
+    def k_atten(s, st):        # HU -> attenuation (sdct:6-13), elementwise
+        _native.check(lib.lr_atten_coef(vp(s["moving"]), nv, vp(s["warped"]), st), "atten")
+
+    def k_idmap(s, st):        # identity map (net_utils.py:59-87), write-only
+        _native.check(lib.lr_identity_map(*VOL, vp(s["gphi"]), st), "idmap")
+
+    units = {"atten": (k_atten, nv, 8 * nv), "idmap": (k_idmap, nv, 12 * nv), "reg": (k_reg, nv, 12 * nv), "reg_bwd": (k_reg_bwd, nv, 24 * nv), "ncc": (k_ncc, nv, 8 * nv), "ncc_bwd": (k_ncc_bwd, nv, 12 * nv), "warp": (k_warp, batch * nv, batch * 20 * nv), "pca": (k_pca, 3 * nv, 4 * 3 * nv * 56 + 8 * 3 * nv),
              "pca_bwd": (k_pca_bwd, 3 * nv, 4 * 3 * nv * 56 + 4 * 3 * nv), "warp_bwd": (k_warp_bwd, nv, 32 * nv),
              "drr_bwd": (k_drr_bwd, P * 240 * 240 * VOL[1], 4 * nv + 4 * P * 240 * 240), "backproject": (k_backproject, batch * P * nv, batch * (4 * P * nv + 4 * P * DET[0] * DET[1])),
              "backproject_planned": (k_backproject_planned, batch * P * nv, batch * (4 * P * nv + 4 * P * DET[0] * DET[1])),
