@@ -683,11 +683,20 @@ __global__ void __launch_bounds__(WARP_TX * WARP_TY) identity_map_kernel(float *
     out[2 * (int64_t)g.nvox + vox] = ident.x[threadIdx.x];
 }
 
-__global__ void atten_coef_kernel(const float *__restrict__ hu, float *__restrict__ mu, int64_t n) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        float v = fmaxf(hu[i], -1000.0f);                                     // sdct:8
-        mu[i] = mul_rn(div_rn(add_rn(v, 1000.0f), 1000.0f), 0.2f);            // sdct:9
+__device__ __forceinline__ float atten_one(float hu, ConstDiv k1000) {
+    const float v = fmaxf(hu, -1000.0f);                                      // sdct:8
+    return mul_rn(div_const(add_rn(v, 1000.0f), k1000), 0.2f);                // sdct:9 (division by a constant: bit-identical to IEEE)
+}
+
+// n4 float4 groups (16-byte-aligned pointers) + a scalar tail
+__global__ void __launch_bounds__(256) atten_coef_kernel(const float *__restrict__ hu, float *__restrict__ mu, int64_t n, int64_t n4, ConstDiv k1000) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t i = t; i < n4; i += stride) {
+        float4 v = ld_stream4(reinterpret_cast<const float4 *>(hu) + i);
+        v.x = atten_one(v.x, k1000); v.y = atten_one(v.y, k1000); v.z = atten_one(v.z, k1000); v.w = atten_one(v.w, k1000);
+        st_stream4(reinterpret_cast<float4 *>(mu) + i, v);
     }
+    for (int64_t i = 4 * n4 + t; i < n; i += stride) mu[i] = atten_one(hu[i], k1000);
 }
 
 static WarpDims make_dims(int C, int D, int H, int W, int z_begin = 0, int z_count = -1) {
@@ -928,7 +937,10 @@ extern "C" int lr_identity_map(int D, int H, int W, float *out, lr_stream_t stre
 extern "C" int lr_atten_coef(const float *hu, int64_t n, float *mu, lr_stream_t stream) {
     LR_REQUIRE(hu && mu && n >= 0, "atten_coef: bad argument");
     if (n == 0) return LR_OK;
-    int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
-    atten_coef_kernel<<<blocks, 256, 0, as_stream(stream)>>>(hu, mu, n);
+    const bool vec = ((uintptr_t)hu % 16 == 0) && ((uintptr_t)mu % 16 == 0);
+    const int64_t n4 = vec ? n / 4 : 0, work = n4 + (n - 4 * n4);
+    const int64_t cap = (int64_t)sm_count() * 8;
+    const int blocks = (int)((work + 255) / 256 < cap ? (work + 255) / 256 : cap);
+    atten_coef_kernel<<<blocks, 256, 0, as_stream(stream)>>>(hu, mu, n, n4, make_const_div(1000.0f));
     return check_launch("atten_coef_kernel");
 }

@@ -755,6 +755,21 @@ def test_remaining_mirror_entry_points(dev):
     assert per_image_rel_l2(pr.project_numpy(d2["vol"], d2["poses"], d2["resolution"], d2["spacing"]), d2["proj"]) <= TOL
 
 
+@pytest.mark.parametrize("n,offset", [(1, 0), (3, 0), (4, 0), (1027, 0), (1027, 1), (64 * 64 * 64 + 5, 0), (4099, 3)])
+def test_atten_coef_vector_and_tail_paths_bit_exact(dev, n, offset):
+    """HU -> attenuation (sdct:6-13): float4 groups + scalar tail, and the scalar path for a pointer that is not 16-byte
+    aligned, bit for bit against the oracle; in place like the reference (the clamp is visible in the input)."""
+    from liftreg_b200 import ops
+    from oracle import c_oracle
+    rs = np.random.RandomState(13)
+    hu = rs.uniform(-1500.0, 2500.0, n + offset).astype(np.float32)
+    t = cu(hu.copy(), dev)
+    view = t[offset:]
+    ops.atten_coef_(view)
+    assert np.array_equal(view.cpu().numpy(), c_oracle.atten_coef(hu[offset:].copy()))
+    assert np.array_equal(t[:offset].cpu().numpy(), hu[:offset])
+
+
 # ------------------------------------------------------------------ PCA-subspace decode (row f2)
 @pytest.mark.parametrize("B,K,shape", [(1, 56, (6, 5, 7)), (3, 56, (20, 24, 28)), (8, 8, (4, 4, 4)), (33, 60, (5, 6, 7)), (2, 4, (3, 3, 3)),
                                        (2, 3, (9, 8, 7)), (5, 57, (12, 10, 11)), (1, 1, (2, 2, 2))])
