@@ -144,6 +144,11 @@ __device__ __forceinline__ void st_stream4(float4 *p, float4 v) {
 __device__ __forceinline__ void red_add(float *p, float v) {
     asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
+// the same under a predicate that lives inside the instruction (@p RED): the compiler branches around an `asm volatile`
+// instead of predicating it, which costs BSSY + BRA + BSYNC per conditional reduction
+__device__ __forceinline__ void red_add_if(bool on, float *p, float v) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q red.global.add.f32 [%0], %1;\n\t}" ::"l"(p), "f"(v), "r"((unsigned)on) : "memory");
+}
 
 }  // namespace lr
 

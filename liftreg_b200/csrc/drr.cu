@@ -487,13 +487,13 @@ __global__ void __launch_bounds__(32 * DRR_ROWS)
         }
         if (recv) m |= (m_p >> 1) & 0x55u;
         if (give) m &= 0x55u;
-        if (leader) {
-            float *b = V + key;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const int off = (c & 1) + ((c >> 1) & 1) * sy + (c >> 2) * sz;
-                if ((m >> c) & 1u) red_add(b + off, val[c]);
-            }
+        {   // predicated reductions, four row pointers with immediate +4 offsets (dead lanes: leader == false, any address)
+            if (!leader) m = 0u;
+            float *b0 = V + (leader ? key : 0), *b1 = b0 + sy, *b2 = b0 + sz, *b3 = b2 + sy;
+            red_add_if(m & 1u, b0, val[0]);  red_add_if(m & 2u, b0 + 1, val[1]);
+            red_add_if(m & 4u, b1, val[2]);  red_add_if(m & 8u, b1 + 1, val[3]);
+            red_add_if(m & 16u, b2, val[4]); red_add_if(m & 32u, b2 + 1, val[5]);
+            red_add_if(m & 64u, b3, val[6]); red_add_if(m & 128u, b3 + 1, val[7]);
         }
     }
 }
