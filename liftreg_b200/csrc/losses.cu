@@ -90,7 +90,19 @@ __global__ void __launch_bounds__(NCC_THREADS) ncc_shifted_kernel(const float *_
     const float *xb = x + (int64_t)b * N, *yb = y + (int64_t)b * N;
     const float k = __ldg(xb), l = __ldg(yb);
     float su = 0.0f, sv = 0.0f, suv = 0.0f, suu = 0.0f, svv = 0.0f;
-    for (int64_t i = (int64_t)blockIdx.x * NCC_THREADS + threadIdx.x; i < N; i += (int64_t)gridDim.x * NCC_THREADS) {
+    const int64_t t = (int64_t)blockIdx.x * NCC_THREADS + threadIdx.x, stride = (int64_t)gridDim.x * NCC_THREADS;
+    // 16-byte loads where the item's rows allow it (four times the bytes in flight per thread: the scalar loop was bound by
+    // memory latency at full occupancy, 2.6 TB/s), scalar tail
+    const int64_t n4 = (((uintptr_t)xb | (uintptr_t)yb) % 16 == 0) ? N / 4 : 0;
+    for (int64_t i = t; i < n4; i += stride) {
+        const float4 a = ld_stream4(reinterpret_cast<const float4 *>(xb) + i), c = ld_stream4(reinterpret_cast<const float4 *>(yb) + i);
+        const float u0 = a.x - k, u1 = a.y - k, u2 = a.z - k, u3 = a.w - k, v0 = c.x - l, v1 = c.y - l, v2 = c.z - l, v3 = c.w - l;
+        su += (u0 + u1) + (u2 + u3); sv += (v0 + v1) + (v2 + v3);
+        suv = fmaf(u0, v0, fmaf(u1, v1, fmaf(u2, v2, fmaf(u3, v3, suv))));
+        suu = fmaf(u0, u0, fmaf(u1, u1, fmaf(u2, u2, fmaf(u3, u3, suu))));
+        svv = fmaf(v0, v0, fmaf(v1, v1, fmaf(v2, v2, fmaf(v3, v3, svv))));
+    }
+    for (int64_t i = 4 * n4 + t; i < N; i += stride) {
         const float u = ld_stream(xb + i) - k, v = ld_stream(yb + i) - l;
         su += u; sv += v;
         suv = fmaf(u, v, suv); suu = fmaf(u, u, suu); svv = fmaf(v, v, svv);
@@ -130,7 +142,18 @@ __global__ void __launch_bounds__(NCC_THREADS) ncc_backward_kernel(const float *
     const float f1 = (float)(scale * c1), f2 = (float)(scale * c2), f3 = (float)(scale * c3);
     const float *xb = x + (int64_t)b * N, *yb = y + (int64_t)b * N;
     float *gb = gx + (int64_t)b * N;
-    for (int64_t i = (int64_t)blockIdx.x * NCC_THREADS + threadIdx.x; i < N; i += (int64_t)gridDim.x * NCC_THREADS) {
+    const int64_t t = (int64_t)blockIdx.x * NCC_THREADS + threadIdx.x, stride = (int64_t)gridDim.x * NCC_THREADS;
+    const int64_t n4 = (((uintptr_t)xb | (uintptr_t)yb | (uintptr_t)gb) % 16 == 0) ? N / 4 : 0;
+    for (int64_t i = t; i < n4; i += stride) {
+        const float4 xv = ld_stream4(reinterpret_cast<const float4 *>(xb) + i), yv = ld_stream4(reinterpret_cast<const float4 *>(yb) + i);
+        float4 o;
+        o.x = fmaf(f1, centred(yv.x, my), fmaf(-f2, centred(xv.x, mx), -f3));
+        o.y = fmaf(f1, centred(yv.y, my), fmaf(-f2, centred(xv.y, mx), -f3));
+        o.z = fmaf(f1, centred(yv.z, my), fmaf(-f2, centred(xv.z, mx), -f3));
+        o.w = fmaf(f1, centred(yv.w, my), fmaf(-f2, centred(xv.w, mx), -f3));
+        st_stream4(reinterpret_cast<float4 *>(gb) + i, o);
+    }
+    for (int64_t i = 4 * n4 + t; i < N; i += stride) {
         const float a = centred(ld_stream(xb + i), mx), c = centred(ld_stream(yb + i), my);
         st_stream(gb + i, fmaf(f1, c, fmaf(-f2, a, -f3)));
     }
