@@ -670,17 +670,21 @@ __global__ void __launch_bounds__(WARP_TX * WARP_TY, LR_WARP_BWD_MINBLOCKS)
     }
 }
 
+constexpr int IDENT_PLANES = 8;
 __global__ void __launch_bounds__(WARP_TX * WARP_TY) identity_map_kernel(float *__restrict__ out, WarpDims g) {
     __shared__ IdentTable<WARP_TY> ident;
     const int x = blockIdx.x * WARP_TX + threadIdx.x;
     const int y = blockIdx.y * WARP_TY + threadIdx.y;
-    const int z = blockIdx.z;
-    build_ident_table(ident, g, blockIdx.x * WARP_TX, blockIdx.y * WARP_TY, z);
+    build_ident_table(ident, g, blockIdx.x * WARP_TX, blockIdx.y * WARP_TY, 0);      // x / y tables once per block
     if (x >= g.W || y >= g.H) return;
-    const int vox = z * g.HW + y * g.W + x;
-    out[vox] = ident.z;
-    out[(int64_t)g.nvox + vox] = ident.y[threadIdx.y];
-    out[2 * (int64_t)g.nvox + vox] = ident.x[threadIdx.x];
+    const float cy = ident.y[threadIdx.y], cx = ident.x[threadIdx.x];
+    const int z_end = min(g.D, ((int)blockIdx.z + 1) * IDENT_PLANES);
+    for (int z = blockIdx.z * IDENT_PLANES; z < z_end; ++z) {                         // a run of planes per block: 1.5 KB per block
+        const int vox = z * g.HW + y * g.W + x;                                       // and plane was mostly launch overhead
+        st_stream(out + vox, identity_coord(z, g.sp0));
+        st_stream(out + (int64_t)g.nvox + vox, cy);
+        st_stream(out + 2 * (int64_t)g.nvox + vox, cx);
+    }
 }
 
 __device__ __forceinline__ float atten_one(float hu, ConstDiv k1000) {
@@ -930,7 +934,7 @@ extern "C" int lr_identity_map(int D, int H, int W, float *out, lr_stream_t stre
     LR_REQUIRE(D > 1 && H > 1 && W > 1 && D <= 65535, "identity_map: each size must be in [2, 65535]");
     LR_REQUIRE((int64_t)D * H * W < (1ll << 31), "identity_map: D*H*W must fit 32 bits");
     WarpDims g = make_dims(1, D, H, W);
-    identity_map_kernel<<<warp_grid(1, D, H, W), dim3(WARP_TX, WARP_TY), 0, as_stream(stream)>>>(out, g);
+    identity_map_kernel<<<warp_grid(1, (D + IDENT_PLANES - 1) / IDENT_PLANES, H, W), dim3(WARP_TX, WARP_TY), 0, as_stream(stream)>>>(out, g);
     return check_launch("identity_map_kernel");
 }
 
